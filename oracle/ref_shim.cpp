@@ -1,0 +1,168 @@
+// oracle/ref_shim.cpp — TEST INFRASTRUCTURE ONLY. Not part of the product.
+//
+// Exposes the UNMODIFIED reference implementation (compiled from /root/reference/source/ogmaneo/*.cpp where it
+// lies, namespace renamed with -Dogmaneo=ogmaneo_ref, see oracle/Makefile) through the flat hierarchy C ABI of
+// include/ogn_hierarchy_api.h with the prefix oref_. It is used to (1) pin oracle/sph_oracle.cpp, (2) generate
+// the fixtures under tests/golden/, (3) act as the parity checker in tests/ and (4) be the CPU baseline
+// (`cpu_baseline.kind == "reference"`) in bench.py. Nothing under ogmaneo2_b200/ may link or load this.
+//
+// No reference source is copied: this file only includes the reference's public headers at build time.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <istream>
+#include <memory>
+#include <ostream>
+#include <random>
+#include <string>
+#include <vector>
+#include <omp.h>
+
+// The reference keeps Predictor::hiddenActivations and Actor::hiddenValues private with no getter; the parity
+// tests compare them, so open the classes up for this one translation unit (layout is unaffected).
+#define private public
+#include <ogmaneo/Hierarchy.h>
+#undef private
+
+#include "../include/ogn_hierarchy_api.h"
+
+using namespace ogmaneo; // == ogmaneo_ref after macro renaming
+
+namespace {
+struct Handle {
+    ComputeSystem cs;
+    Hierarchy h;
+};
+thread_local std::string g_err;
+int fail(const char *m) { g_err = m; return 1; }
+template <typename T> int copyOut(const std::vector<T> &v, T *out) {
+    if (out) std::memcpy(out, v.data(), v.size() * sizeof(T));
+    return (int)v.size();
+}
+int64_t copyW(const std::vector<float> &v, float *out, int64_t cap) {
+    if (out) std::memcpy(out, v.data(), (size_t)std::min<int64_t>(cap, (int64_t)v.size()) * sizeof(float));
+    return (int64_t)v.size();
+}
+} // namespace
+
+extern "C" {
+OGN_DECLARE_HIERARCHY_API(oref_)
+
+int oref_create(const ogn_hierarchy_desc *d, uint32_t seed, void **out) {
+    try {
+        auto *H = new Handle();
+        H->cs.rng.seed(seed);
+        std::vector<Int3> sizes(d->num_inputs);
+        std::vector<InputType> types(d->num_inputs);
+        for (int i = 0; i < d->num_inputs; i++) {
+            sizes[i] = Int3(d->input_sizes[3 * i], d->input_sizes[3 * i + 1], d->input_sizes[3 * i + 2]);
+            sizes[i].pad = 0;
+            types[i] = (InputType)d->input_types[i];
+        }
+        std::vector<Hierarchy::LayerDesc> lds(d->num_layers);
+        for (int l = 0; l < d->num_layers; l++) {
+            const ogn_layer_desc &s = d->layers[l];
+            lds[l].hiddenSize = Int3(s.hidden_x, s.hidden_y, s.hidden_z);
+            lds[l].hiddenSize.pad = 0;
+            lds[l].ffRadius = s.ff_radius;
+            lds[l].pRadius = s.p_radius;
+            lds[l].ticksPerUpdate = s.ticks_per_update;
+            lds[l].temporalHorizon = s.temporal_horizon;
+            lds[l].aRadius = s.a_radius;
+            lds[l].historyCapacity = s.history_capacity;
+        }
+        H->h.initRandom(H->cs, sizes, types, lds);
+        *out = H;
+        return 0;
+    } catch (const std::exception &e) {
+        return fail(e.what());
+    }
+}
+void oref_destroy(void *h) { delete (Handle *)h; }
+const char *oref_last_error(void) { return g_err.c_str(); }
+int oref_set_num_threads(int n) { ComputeSystem::setNumThreads(n); return 0; }
+
+int oref_step(void *hh, const int *const *input_cs, int learn, float reward, int mimic) {
+    Handle *H = (Handle *)hh;
+    const std::vector<Int3> &sz = H->h.getInputSizes();
+    std::vector<IntBuffer> bufs(sz.size());
+    std::vector<const IntBuffer *> ptrs(sz.size());
+    for (size_t i = 0; i < sz.size(); i++) {
+        bufs[i].assign(input_cs[i], input_cs[i] + sz[i].x * sz[i].y);
+        ptrs[i] = &bufs[i];
+    }
+    H->h.step(H->cs, ptrs, learn != 0, reward, mimic != 0);
+    return 0;
+}
+int oref_num_layers(void *h) { return ((Handle *)h)->h.getNumLayers(); }
+int oref_get_update(void *h, int l) { return ((Handle *)h)->h.getUpdate(l); }
+int oref_get_ticks(void *h, int l) { return ((Handle *)h)->h.getTicks(l); }
+int oref_get_ticks_per_update(void *h, int l) { return ((Handle *)h)->h.getTicksPerUpdate(l); }
+int oref_get_prediction_cs(void *hh, int i, int *out) {
+    Hierarchy &h = ((Handle *)hh)->h;
+    if (h.getALayers()[i] == nullptr && h.getPLayers(0)[i] == nullptr) return -1;
+    return copyOut(h.getPredictionCs(i), out);
+}
+int oref_sc_hidden_cs(void *h, int l, int *out) { return copyOut(((Handle *)h)->h.getSCLayer(l).getHiddenCs(), out); }
+int oref_sc_hidden_cs_prev(void *h, int l, int *out) {
+    return copyOut(((Handle *)h)->h.getSCLayer(l).getHiddenCsPrev(), out);
+}
+int oref_sc_num_visible(void *h, int l) { return ((Handle *)h)->h.getSCLayer(l).getNumVisibleLayers(); }
+int64_t oref_sc_weights(void *h, int l, int vli, float *out, int64_t cap) {
+    return copyW(((Handle *)h)->h.getSCLayer(l).getVisibleLayer(vli).weights.nonZeroValues, out, cap);
+}
+int oref_sc_reconstructions(void *h, int l, int vli, float *out) {
+    return copyOut(((Handle *)h)->h.getSCLayer(l).getVisibleLayer(vli).reconstructions, out);
+}
+int oref_pred_count(void *h, int l) { return (int)((Handle *)h)->h.getPLayers(l).size(); }
+int oref_pred_exists(void *h, int l, int p) { return ((Handle *)h)->h.getPLayers(l)[p] != nullptr; }
+int oref_pred_hidden_cs(void *h, int l, int p, int *out) {
+    return copyOut(((Handle *)h)->h.getPLayers(l)[p]->getHiddenCs(), out);
+}
+int oref_pred_activations(void *h, int l, int p, float *out) {
+    return copyOut(((Handle *)h)->h.getPLayers(l)[p]->hiddenActivations, out);
+}
+int oref_pred_num_visible(void *h, int l, int p) { return ((Handle *)h)->h.getPLayers(l)[p]->getNumVisibleLayers(); }
+int64_t oref_pred_weights(void *h, int l, int p, int vli, float *out, int64_t cap) {
+    return copyW(((Handle *)h)->h.getPLayers(l)[p]->getVisibleLayer(vli).weights.nonZeroValues, out, cap);
+}
+int oref_pred_input_cs_prev(void *h, int l, int p, int vli, int *out) {
+    return copyOut(((Handle *)h)->h.getPLayers(l)[p]->getVisibleLayer(vli).inputCsPrev, out);
+}
+int oref_actor_exists(void *h, int p) { return ((Handle *)h)->h.getALayers()[p] != nullptr; }
+int oref_actor_hidden_cs(void *h, int p, int *out) { return copyOut(((Handle *)h)->h.getALayers()[p]->getHiddenCs(), out); }
+int oref_actor_values(void *h, int p, float *out) { return copyOut(((Handle *)h)->h.getALayers()[p]->hiddenValues, out); }
+int oref_actor_num_visible(void *h, int p) { return ((Handle *)h)->h.getALayers()[p]->getNumVisibleLayers(); }
+int64_t oref_actor_weights(void *h, int p, int vli, int which, float *out, int64_t cap) {
+    const Actor::VisibleLayer &vl = ((Handle *)h)->h.getALayers()[p]->getVisibleLayer(vli);
+    return copyW(which == 0 ? vl.valueWeights.nonZeroValues : vl.actionWeights.nonZeroValues, out, cap);
+}
+int oref_set_sc_alpha(void *h, int l, float a) { ((Handle *)h)->h.getSCLayer(l).alpha = a; return 0; }
+int oref_set_pred_alpha(void *h, int l, int p, float a) { ((Handle *)h)->h.getPLayers(l)[p]->alpha = a; return 0; }
+int oref_set_actor_params(void *h, int p, float alpha, float beta, float gamma, int minSteps, int historyIters) {
+    Actor &a = *((Handle *)h)->h.getALayers()[p];
+    a.alpha = alpha; a.beta = beta; a.gamma = gamma; a.minSteps = minSteps; a.historyIters = historyIters;
+    return 0;
+}
+int64_t oref_save(void *h, const char *path) {
+    std::ofstream os(path, std::ios::binary);
+    if (!os) return -1;
+    ((Handle *)h)->h.writeToStream(os);
+    return (int64_t)os.tellp();
+}
+int oref_load(const char *path, uint32_t seed, void **out) {
+    std::ifstream is(path, std::ios::binary);
+    if (!is) return fail("cannot open file");
+    auto *H = new Handle();
+    H->cs.rng.seed(seed);
+    H->h.readFromStream(is);
+    *out = H;
+    return 0;
+}
+uint32_t oref_rng_peek(void *h) {
+    std::mt19937 c = ((Handle *)h)->cs.rng;
+    return (uint32_t)c();
+}
+} // extern "C"
