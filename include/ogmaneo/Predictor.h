@@ -1,0 +1,69 @@
+// include/ogmaneo/Predictor.h — B200-native drop-in for the reference's <ogmaneo/Predictor.h> (:15-150).
+// Same public interface; state and weights live in HBM; learn()/activate() launch the fused sm_100a kernel
+// K6+K7+K8 (include/ogn_kernels_api.h). Host members returned by getters are lazily refreshed mirrors.
+#pragma once
+
+#include "ComputeSystem.h"
+
+namespace ogmaneo {
+class Predictor {
+public:
+    struct VisibleLayerDesc {
+        Int3 size;
+        int radius;
+        VisibleLayerDesc() : size(4, 4, 16), radius(2) {}
+    };
+
+    struct VisibleLayer {
+        SparseMatrix weights;  // host mirror (on demand)
+        IntBuffer inputCsPrev; // host mirror: the inputs seen by the previous activate()
+    };
+
+    struct Impl;
+
+    float alpha; // learning rate
+
+    Predictor();
+    Predictor(const Predictor &other);
+    Predictor &operator=(const Predictor &other);
+    ~Predictor();
+
+    // Predictor.cpp:72-109 — weights U(-0.01,0.01)
+    void initRandom(ComputeSystem &cs, const Int3 &hiddenSize, const std::vector<VisibleLayerDesc> &visibleLayerDescs);
+    // Predictor.cpp:111-127
+    void activate(ComputeSystem &cs, const std::vector<const IntBuffer *> &inputCs);
+    // Predictor.cpp:129-135
+    void learn(ComputeSystem &cs, const IntBuffer *hiddenTargetCs);
+
+    void writeToStream(std::ostream &os) const; // Predictor.cpp:137-162
+    void readFromStream(std::istream &is);      // Predictor.cpp:164-192
+
+    int getNumVisibleLayers() const { return (int)visibleLayerDescs.size(); }
+    const VisibleLayer &getVisibleLayer(int i) const;
+    const VisibleLayerDesc &getVisibleLayerDesc(int i) const { return visibleLayerDescs[i]; }
+    const IntBuffer &getHiddenCs() const;
+    const Int3 &getHiddenSize() const { return hiddenSize; }
+
+    // --- extensions ---
+    const FloatBuffer &getHiddenActivations() const; // private in the reference (Predictor.h:42)
+    void getWeights(int i, std::vector<float> &out) const;
+    const IntBuffer &getInputCsPrev(int i) const;
+    void initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize, const std::vector<VisibleLayerDesc> &visibleLayerDescs,
+                          int batch, int member);
+    // learn (optional) + activate (optional) as ONE kernel launch on device-resident CSDRs (int32 [member][columns]).
+    void stepDevice(ComputeSystem &cs, bool learn, const int *targetCsDevice, bool activate, const int *const *inputCsDevice);
+    const int *hiddenCsDevice() const;
+    void readFromStream(std::istream &is, ComputeSystem &cs);
+    void setState(const IntBuffer &hiddenCs, const std::vector<IntBuffer> &inputCsPrev);
+
+private:
+    Int3 hiddenSize;
+    std::vector<VisibleLayerDesc> visibleLayerDescs;
+    mutable FloatBuffer hiddenActivations;
+    mutable IntBuffer hiddenCs;
+    mutable std::vector<VisibleLayer> visibleLayers;
+    Impl *impl;
+
+    friend class Hierarchy;
+};
+} // namespace ogmaneo

@@ -1,0 +1,56 @@
+/* ogn_b200.h — product-only entry points of libogn_b200.so, on top of the flat hierarchy ABI
+ * (ogn_hierarchy_api.h). These have no counterpart in the reference: they expose what a device-resident
+ * implementation can do beyond Hierarchy::step on host buffers — stepping on inputs already in HBM, ensembles of
+ * lock-stepped hierarchies (BASELINE config 5), x-slab sharding of large layers across GPUs (config 4) and a
+ * device-side weight init for sizes the reference cannot construct. All functions return 0 / non-zero like the flat
+ * ABI; ogn_last_error() has the message.
+ */
+#ifndef OGN_B200_H
+#define OGN_B200_H
+
+#include "ogn_hierarchy_api.h"
+#include "ogn_kernels_api.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Called after a layer wrote its x-slab of a CSDR into `buffer` ([shard_world][count_per_rank] int32, this rank's slab
+ * in place): must complete `buffer` on every rank, ordered on `stream` (cudaStream_t) — e.g. ncclAllGather in place,
+ * torch.distributed.all_gather_into_tensor on that stream, or a peer-memory kernel. */
+typedef void (*ogn_all_gather_fn)(void *user, int *buffer, int count_per_rank, void *stream);
+
+typedef struct ogn_create_options {
+    int device;            /* CUDA device ordinal, -1 = current */
+    int device_init;       /* 0: weights drawn from std::mt19937 in the reference's order (bit-identical to the reference);
+                              1: counter-hash init on the device keyed by (seed, matrix, CSR index) */
+    int replay_rng;        /* 1: replay every runKernelN seed draw so ComputeSystem::rng tracks the reference exactly
+                              (always on when the hierarchy has an Actor) */
+    int shard_rank, shard_world; /* x-slab sharding of every layer over shard_world devices (one process per device) */
+    ogn_all_gather_fn all_gather;
+    void *all_gather_user;
+    int ensemble;          /* number of independent lock-stepped hierarchies (>= 1) */
+    const uint32_t *ensemble_seeds; /* optional [ensemble]; default seed + k */
+} ogn_create_options;
+
+/* ogn_create with options. ogn_create(desc, seed, out) == ogn_create_ex with {device -1, device_init 0, replay_rng 1}. */
+int ogn_create_ex(const ogn_hierarchy_desc *desc, uint32_t seed, const ogn_create_options *opt, void **out);
+
+/* Hierarchy::step on inputs that already live in device memory (int32 [member][columns] per input). Fully asynchronous
+ * on the hierarchy's stream: nothing is copied to or from the host. */
+int ogn_step_device(void *h, const int *const *input_cs_dev, int learn_enabled, float reward, int mimic);
+/* Device pointer of the prediction CSDR of input i ([member][columns]); valid for the life of the handle. */
+const int *ogn_prediction_cs_device(void *h, int i);
+/* The cudaStream_t all work of this hierarchy is queued on / wait for it to drain. */
+void *ogn_stream(void *h);
+int ogn_synchronize(void *h);
+int ogn_ensemble_size(void *h);
+/* (hidden column, visible column) pairs whose weights SparseCoder l rewrote since the last call: the data-dependent
+ * term U of the algorithmic byte count. Synchronises. */
+uint64_t ogn_take_sc_update_count(void *h, int l);
+int ogn_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OGN_B200_H */

@@ -1,0 +1,282 @@
+// csrc/host/Device.cpp — CUDA context, geometry tables and weight sets (see Device.h).
+#include "Device.h"
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace ogmaneo {
+namespace detail {
+
+void cudaCheck(cudaError_t e, const char *what) {
+    if (e != cudaSuccess)
+        throw std::runtime_error(std::string("ogmaneo-b200: ") + what + ": " + cudaGetErrorString(e) +
+                                 " (this build has no CPU fallback)");
+}
+
+DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
+    int count = 0;
+    cudaCheck(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
+    if (count == 0) throw std::runtime_error("ogmaneo-b200: no CUDA device visible (this build has no CPU fallback)");
+    if (device < 0) cudaCheck(cudaGetDevice(&device), "cudaGetDevice");
+    cudaCheck(cudaSetDevice(device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    cudaCheck(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        throw std::runtime_error("ogmaneo-b200: device " + std::to_string(device) + " (" + prop.name +
+                                 ") is not compute capability 10.x; the kernels are built for sm_100a only");
+    cudaCheck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+}
+
+DeviceContext::~DeviceContext() {
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+void Geometry::build(const Int3 &hidden, const Int3 &visible, int r) {
+    Hx = hidden.x; Hy = hidden.y; Hz = hidden.z; Vx = visible.x; Vy = visible.y; Vz = visible.z; radius = r;
+    // project(): (int)(pos * (float)in / (float)out + 0.5f)   (Helpers.h:223-228, Helpers.cpp:245-246)
+    const float sx = (float)Vx / (float)Hx, syf = (float)Vy / (float)Hy;
+    auto axis = [r](int H, int V, float scale, std::vector<int> &lo, std::vector<int> &n, std::vector<int> &p, std::vector<int> &rlo,
+                    std::vector<int> &rhi) {
+        lo.resize(H); n.resize(H); p.resize(H);
+        rlo.assign(V, H); rhi.assign(V, -1);
+        int acc = 0;
+        for (int o = 0; o < H; o++) {
+            const int c = (int)(o * scale + 0.5f);
+            const int a = std::max(0, c - r), b = std::min(V - 1, c + r);
+            lo[o] = a; n[o] = std::max(0, b - a + 1); p[o] = acc; acc += n[o];
+            for (int i = a; i <= b; i++) { rlo[i] = std::min(rlo[i], o); rhi[i] = std::max(rhi[i], o); }
+        }
+        return acc;
+    };
+    const int sxTotal = axis(Hx, Vx, sx, lox, nx, px, rlox, rhix);
+    sy = axis(Hy, Vy, syf, loy, ny, py, rloy, rhiy);
+    nnz = (int64_t)Vz * Hz * (int64_t)sxTotal * sy;
+
+    std::vector<int> all;
+    auto push = [&all](const std::vector<int> &v) { size_t o = all.size(); all.insert(all.end(), v.begin(), v.end()); return o; };
+    const size_t o0 = push(lox), o1 = push(nx), o2 = push(px), o3 = push(loy), o4 = push(ny), o5 = push(py), o6 = push(rlox),
+                 o7 = push(rhix), o8 = push(rloy), o9 = push(rhiy);
+    tables_.alloc(all.size());
+    cudaCheck(cudaMemcpy(tables_.ptr(), all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice), "geometry H2D");
+    const int *t = tables_.ptr();
+    host.Hx = Hx; host.Hy = Hy; host.Hz = Hz; host.Vx = Vx; host.Vy = Vy; host.Vz = Vz; host.radius = r; host.sy = sy;
+    host.lox = t + o0; host.nx = t + o1; host.px = t + o2; host.loy = t + o3; host.ny = t + o4; host.py = t + o5;
+    host.rlox = t + o6; host.rhix = t + o7; host.rloy = t + o8; host.rhiy = t + o9;
+    devStruct_.alloc(1);
+    cudaCheck(cudaMemcpy(devStruct_.ptr(), &host, sizeof(ogn_rf), cudaMemcpyHostToDevice), "geometry H2D");
+    dev = devStruct_.ptr();
+}
+
+std::shared_ptr<Geometry> Geometry::get(const Int3 &hidden, const Int3 &visible, int radius) {
+    // one table set per (device, shape): layers with temporalHorizon > 1 share it
+    typedef std::tuple<int, int, int, int, int, int, int, int> Key;
+    static std::mutex mtx;
+    static std::map<Key, std::weak_ptr<Geometry>> cache;
+    int device = 0;
+    cudaCheck(cudaGetDevice(&device), "cudaGetDevice");
+    Key k(device, hidden.x, hidden.y, hidden.z, visible.x, visible.y, visible.z, radius);
+    std::lock_guard<std::mutex> lock(mtx);
+    if (auto sp = cache[k].lock()) return sp;
+    auto sp = std::shared_ptr<Geometry>(new Geometry());
+    sp->build(hidden, visible, radius);
+    cache[k] = sp;
+    return sp;
+}
+
+void Geometry::visibleRange(int a, int b, int &lo, int &hi) const {
+    lo = Vx; hi = 0;
+    for (int o = a; o < b; o++)
+        if (nx[o] > 0) { lo = std::min(lo, lox[o]); hi = std::max(hi, lox[o] + nx[o]); }
+    if (hi < lo) lo = hi = 0;
+}
+void Geometry::hiddenCover(int a, int b, int &lo, int &hi) const {
+    lo = Hx; hi = 0;
+    for (int v = a; v < b; v++)
+        if (rhix[v] >= rlox[v]) { lo = std::min(lo, rlox[v]); hi = std::max(hi, rhix[v] + 1); }
+    if (hi < lo) lo = hi = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+void WeightSet::allocate(DeviceContext &ctx, std::shared_ptr<Geometry> g, int batch_, bool hasR_, bool hasRecon, int a, int b) {
+    geo = g; batch = batch_; hasR = hasR_; fx0 = a; fx1 = b;
+    const bool whole = (a == 0 && b == g->Hx);
+    if (whole) { vx0 = 0; vx1 = g->Vx; rx0 = 0; rx1 = g->Hx; }
+    else {
+        g->visibleRange(a, b, vx0, vx1);     // visible columns whose reconstruction touches an owned hidden column
+        g->hiddenCover(vx0, vx1, rx0, rx1);  // every hidden column those reconstructions sum over (replicas)
+    }
+    wf.alloc((size_t)(fCount() * batch));
+    if (hasR) wr.alloc((size_t)(rCount() * batch));
+    if (hasRecon) recon.allocZero((size_t)g->Vx * g->Vy * g->Vz * batch, ctx.stream);
+}
+
+ogn_wset WeightSet::desc() const {
+    ogn_wset d;
+    std::memset(&d, 0, sizeof(d));
+    d.rf = geo->dev;
+    d.wf = wf.ptr(); d.wr = wr.ptr(); d.recon = recon.ptr();
+    d.wf_base = geo->xBlock(fx0); d.wr_base = hasR ? geo->xBlock(rx0) : 0;
+    d.wf_mstride = fCount(); d.wr_mstride = rCount();
+    d.fx0 = fx0; d.fx1 = fx1; d.rx0 = rx0; d.rx1 = rx1; d.vx0 = vx0; d.vx1 = vx1;
+    return d;
+}
+
+namespace {
+const int64_t kStageFloats = 32ll << 20; // 128 MB staging chunks
+}
+
+void WeightSet::fillFromCSRStream(DeviceContext &ctx, int member, const std::function<void(float *, int64_t)> &fill) {
+    const Geometry &g = *geo;
+    const ogn_wset d = desc();
+    const int ncolsAll = g.Hx * g.Hy;
+    std::vector<float> host;
+    DevBuf<float> stage;
+    stage.alloc((size_t)std::min<int64_t>(kStageFloats, std::max<int64_t>(g.nnz, 1)));
+    int col = 0;
+    while (col < ncolsAll) {
+        // largest run of whole columns that fits the staging buffer (at least one column)
+        int end = col;
+        const int64_t base = g.colBlock(col / g.Hy, col % g.Hy);
+        int64_t n = 0;
+        while (end < ncolsAll) {
+            const int64_t blk = (int64_t)g.slots(end / g.Hy, end % g.Hy) * g.Vz * g.Hz;
+            if (n + blk > (int64_t)stage.size() && end > col) break;
+            n += blk; end++;
+        }
+        if (n > (int64_t)stage.size()) stage.alloc((size_t)n);
+        host.resize((size_t)n);
+        fill(host.data(), n);
+        const int xa = col / g.Hy, xb = (end - 1) / g.Hy + 1; // hidden x touched by this chunk
+        const bool needF = xa < fx1 && xb > fx0, needR = hasR && xa < rx1 && xb > rx0;
+        if (needF || needR) {
+            cudaCheck(cudaMemcpyAsync(stage.ptr(), host.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx.stream), "H2D");
+            if (needF) {
+                const int c0 = std::max(col, fx0 * g.Hy), c1 = std::min(end, fx1 * g.Hy);
+                kernelCheck(ogn_weights_from_csr(&d, &g.host, member, 0, c0, c1, stage.ptr(), base, ctx.stream), "weights_from_csr F");
+            }
+            if (needR) {
+                const int c0 = std::max(col, rx0 * g.Hy), c1 = std::min(end, rx1 * g.Hy);
+                kernelCheck(ogn_weights_from_csr(&d, &g.host, member, 1, c0, c1, stage.ptr(), base, ctx.stream), "weights_from_csr R");
+            }
+            ctx.sync(); // `host` and `stage` are reused by the next chunk
+        }
+        col = end;
+    }
+}
+
+void WeightSet::uploadCSR(DeviceContext &ctx, int member, const float *csrAll) {
+    int64_t pos = 0;
+    fillFromCSRStream(ctx, member, [&](float *dst, int64_t n) { std::memcpy(dst, csrAll + pos, (size_t)n * sizeof(float)); pos += n; });
+}
+
+void WeightSet::downloadCSR(DeviceContext &ctx, int member, float *out) const {
+    const Geometry &g = *geo;
+    const ogn_wset d = desc();
+    DevBuf<float> stage;
+    stage.alloc((size_t)std::min<int64_t>(kStageFloats, std::max<int64_t>(fCount(), 1)));
+    int col = fx0 * g.Hy;
+    const int colEnd = fx1 * g.Hy;
+    while (col < colEnd) {
+        int end = col;
+        const int64_t base = g.colBlock(col / g.Hy, col % g.Hy);
+        int64_t n = 0;
+        while (end < colEnd) {
+            const int64_t blk = (int64_t)g.slots(end / g.Hy, end % g.Hy) * g.Vz * g.Hz;
+            if (n + blk > (int64_t)stage.size() && end > col) break;
+            n += blk; end++;
+        }
+        if (n > (int64_t)stage.size()) stage.alloc((size_t)n);
+        kernelCheck(ogn_weights_to_csr(&d, &g.host, member, 0, col, end, stage.ptr(), base, ctx.stream), "weights_to_csr");
+        cudaCheck(cudaMemcpyAsync(out + base, stage.ptr(), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx.stream), "D2H");
+        ctx.sync();
+        col = end;
+    }
+}
+
+void WeightSet::initHash(DeviceContext &ctx, int member, uint64_t seed, uint32_t streamId, float lo, float hi) {
+    const ogn_wset d = desc();
+    kernelCheck(ogn_weights_init_hash(&d, &geo->host, member, seed, streamId, lo, hi, ctx.stream), "weights_init_hash");
+}
+
+void WeightSet::initialise(DeviceContext &ctx, int member, const WeightInit &wi) {
+    if (wi.cs->deviceInit) {
+        initHash(ctx, member, wi.cs->deviceInitSeed, wi.streamId, wi.lo, wi.hi);
+        return;
+    }
+    std::uniform_real_distribution<float> dist(wi.lo, wi.hi);
+    std::mt19937 &rng = wi.cs->rng;
+    fillFromCSRStream(ctx, member, [&](float *dst, int64_t n) {
+        for (int64_t i = 0; i < n; i++) dst[i] = dist(rng);
+    });
+}
+
+void WeightSet::cloneFrom(DeviceContext &ctx, const WeightSet &o) {
+    geo = o.geo; batch = o.batch; hasR = o.hasR;
+    fx0 = o.fx0; fx1 = o.fx1; rx0 = o.rx0; rx1 = o.rx1; vx0 = o.vx0; vx1 = o.vx1;
+    wf.cloneFrom(o.wf, ctx.stream); wr.cloneFrom(o.wr, ctx.stream); recon.cloneFrom(o.recon, ctx.stream);
+}
+
+void WeightSetArray::commit(DeviceContext &ctx) {
+    std::vector<ogn_wset> h(sets.size());
+    for (size_t i = 0; i < sets.size(); i++) h[i] = sets[i].desc();
+    dev.alloc(h.size());
+    if (!h.empty()) {
+        cudaCheck(cudaMemcpyAsync(dev.ptr(), h.data(), h.size() * sizeof(ogn_wset), cudaMemcpyHostToDevice, ctx.stream), "wset H2D");
+        ctx.sync(); // h is a stack temporary
+    }
+}
+
+void WeightSetArray::cloneFrom(DeviceContext &ctx, const WeightSetArray &o) {
+    sets.clear();
+    sets.resize(o.sets.size());
+    for (size_t i = 0; i < sets.size(); i++) sets[i].cloneFrom(ctx, o.sets[i]);
+    commit(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+void consumeKernel1(ComputeSystem &cs, int size) {
+    if (!cs.replayRng) return;
+    std::uniform_int_distribution<int> seedDist(0, 999999);
+    const int batches = (size + cs.batchSize1 - 1) / cs.batchSize1;
+    for (int i = 0; i < batches; i++) (void)seedDist(cs.rng);
+}
+
+void consumeKernel2(ComputeSystem &cs, int X, int Y, std::vector<int> *seeds) {
+    if (!cs.replayRng && !seeds) return;
+    std::uniform_int_distribution<int> seedDist(0, 999999);
+    const int bx = (X + cs.batchSize2.x - 1) / cs.batchSize2.x, by = (Y + cs.batchSize2.y - 1) / cs.batchSize2.y;
+    if (seeds) seeds->resize((size_t)bx * by);
+    for (int i = 0; i < bx * by; i++) {
+        const int s = seedDist(cs.rng);
+        if (seeds) (*seeds)[i] = s;
+    }
+}
+
+void slabOf(int X, int rank, int world, int &a, int &b) {
+    if (world <= 1) { a = 0; b = X; return; }
+    if (X % world != 0)
+        throw std::runtime_error("ogmaneo-b200: sharding needs every layer's x size to be a multiple of the device count");
+    a = rank * (X / world); b = a + X / world;
+}
+
+} // namespace detail
+
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+int g_numThreads = 1;
+}
+void ComputeSystem::setNumThreads(int numThreads) { g_numThreads = numThreads; } // host threads are irrelevant on the device path
+int ComputeSystem::getNumThreads() { return g_numThreads; }
+
+detail::DeviceContext &ComputeSystem::context() {
+    if (!ctx) ctx = std::make_shared<detail::DeviceContext>(device);
+    else detail::cudaCheck(cudaSetDevice(ctx->device), "cudaSetDevice");
+    return *ctx;
+}
+void ComputeSystem::synchronize() { context().sync(); }
+void *ComputeSystem::stream() { return (void *)context().stream; }
+
+} // namespace ogmaneo

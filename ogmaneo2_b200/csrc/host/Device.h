@@ -1,0 +1,167 @@
+// csrc/host/Device.h — internal plumbing shared by the host classes: CUDA context, device/pinned buffers, the
+// closed-form receptive-field geometry and the device-resident weight sets. Not installed; users see include/ogmaneo.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <ogmaneo/ComputeSystem.h>
+
+#include "../../../include/ogn_kernels_api.h"
+
+namespace ogmaneo {
+namespace detail {
+
+void cudaCheck(cudaError_t e, const char *what);
+inline void kernelCheck(int code, const char *what) { cudaCheck((cudaError_t)code, what); }
+
+// One device + one stream. Created lazily by ComputeSystem::context(); throws if no sm_100 device is usable.
+struct DeviceContext {
+    int device;
+    cudaStream_t stream;
+    explicit DeviceContext(int device);
+    ~DeviceContext();
+    void sync() const { cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize"); }
+};
+
+template <typename T> class DevBuf {
+public:
+    DevBuf() {}
+    ~DevBuf() { release(); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+        return *this;
+    }
+    void alloc(size_t n) {
+        release();
+        n_ = n;
+        if (n) cudaCheck(cudaMalloc((void **)&p_, n * sizeof(T)), "cudaMalloc");
+    }
+    void allocZero(size_t n, cudaStream_t s) {
+        alloc(n);
+        if (n) cudaCheck(cudaMemsetAsync(p_, 0, n * sizeof(T), s), "cudaMemsetAsync");
+    }
+    void release() {
+        if (p_) cudaFree(p_);
+        p_ = nullptr; n_ = 0;
+    }
+    void cloneFrom(const DevBuf &o, cudaStream_t s) {
+        alloc(o.n_);
+        if (n_) cudaCheck(cudaMemcpyAsync(p_, o.p_, n_ * sizeof(T), cudaMemcpyDeviceToDevice, s), "clone D2D");
+    }
+    void upload(const T *h, size_t n, cudaStream_t s, size_t offset = 0) {
+        if (n) cudaCheck(cudaMemcpyAsync(p_ + offset, h, n * sizeof(T), cudaMemcpyHostToDevice, s), "H2D");
+    }
+    void download(T *h, size_t n, cudaStream_t s, size_t offset = 0) const {
+        if (n) cudaCheck(cudaMemcpyAsync(h, p_ + offset, n * sizeof(T), cudaMemcpyDeviceToHost, s), "D2H");
+    }
+    T *ptr() const { return p_; }
+    size_t size() const { return n_; }
+
+private:
+    T *p_ = nullptr;
+    size_t n_ = 0;
+};
+
+template <typename T> class PinnedBuf {
+public:
+    PinnedBuf() {}
+    ~PinnedBuf() { release(); }
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    void alloc(size_t n) {
+        release();
+        n_ = n;
+        if (n) cudaCheck(cudaMallocHost((void **)&p_, n * sizeof(T)), "cudaMallocHost");
+    }
+    void release() {
+        if (p_) cudaFreeHost(p_);
+        p_ = nullptr; n_ = 0;
+    }
+    T *ptr() const { return p_; }
+    size_t size() const { return n_; }
+
+private:
+    T *p_ = nullptr;
+    size_t n_ = 0;
+};
+
+// initSMLocalRF (Helpers.cpp:236-313) in closed form; host tables + their device copies.
+struct Geometry {
+    int Hx = 0, Hy = 0, Hz = 0, Vx = 0, Vy = 0, Vz = 0, radius = 0, sy = 0;
+    std::vector<int> lox, nx, px, loy, ny, py, rlox, rhix, rloy, rhiy;
+    int64_t nnz = 0;
+    ogn_rf host{};       // host copy of the descriptor; its table pointers are device pointers
+    const ogn_rf *dev = nullptr;
+
+    static std::shared_ptr<Geometry> get(const Int3 &hidden, const Int3 &visible, int radius);
+    int64_t colBlock(int ox, int oy) const { return (int64_t)Vz * Hz * ((int64_t)px[ox] * sy + (int64_t)nx[ox] * py[oy]); }
+    int64_t xBlock(int ox) const { return ox >= Hx ? nnz : colBlock(ox, 0); } // offset of column (ox, 0)
+    int slots(int ox, int oy) const { return nx[ox] * ny[oy]; }
+    // visible x range [lo, hi) touched by hidden x in [a, b); hidden x range [lo, hi) covering visible x in [a, b)
+    void visibleRange(int a, int b, int &lo, int &hi) const;
+    void hiddenCover(int a, int b, int &lo, int &hi) const;
+
+private:
+    DevBuf<int> tables_;
+    DevBuf<ogn_rf> devStruct_;
+    void build(const Int3 &hidden, const Int3 &visible, int radius);
+};
+
+// How the weights of a new layer get their initial values.
+struct WeightInit {
+    ComputeSystem *cs;   // mt19937 order (reference parity) when cs->deviceInit == false
+    float lo, hi;        // uniform range
+    uint32_t streamId;   // distinguishes matrices in the counter-hash mode
+};
+
+// Weights of one visible layer of one layer object, resident in HBM.
+struct WeightSet {
+    std::shared_ptr<Geometry> geo;
+    int batch = 1;
+    bool hasR = false;
+    int fx0 = 0, fx1 = 0, rx0 = 0, rx1 = 0, vx0 = 0, vx1 = 0;
+    DevBuf<float> wf, wr, recon;
+
+    void allocate(DeviceContext &ctx, std::shared_ptr<Geometry> g, int batch, bool hasR, bool hasRecon, int fx0, int fx1);
+    ogn_wset desc() const;
+    int64_t fCount() const { return geo->xBlock(fx1) - geo->xBlock(fx0); }
+    int64_t rCount() const { return hasR ? geo->xBlock(rx1) - geo->xBlock(rx0) : 0; }
+    // fill(dst, n) must produce the next n values of the matrix in the reference's CSR value order (whole matrix,
+    // from index 0 to nnz). Values of columns this device does not store are drawn and dropped.
+    void fillFromCSRStream(DeviceContext &ctx, int member, const std::function<void(float *, int64_t)> &fill);
+    void uploadCSR(DeviceContext &ctx, int member, const float *csrAll);
+    // Values of the stored F range written at their global CSR positions in out (size nnz); other entries untouched.
+    void downloadCSR(DeviceContext &ctx, int member, float *out) const;
+    void initHash(DeviceContext &ctx, int member, uint64_t seed, uint32_t streamId, float lo, float hi);
+    void initialise(DeviceContext &ctx, int member, const WeightInit &wi);
+    void cloneFrom(DeviceContext &ctx, const WeightSet &o);
+};
+
+struct WeightSetArray {
+    std::vector<WeightSet> sets;
+    DevBuf<ogn_wset> dev;
+    void commit(DeviceContext &ctx); // (re)upload the descriptor array
+    const ogn_wset *devPtr() const { return dev.ptr(); }
+    void cloneFrom(DeviceContext &ctx, const WeightSetArray &o);
+};
+
+// RNG consumption of the reference's launchers (Helpers.cpp:15-72). seeds != nullptr forces the draws.
+void consumeKernel1(ComputeSystem &cs, int size);
+void consumeKernel2(ComputeSystem &cs, int X, int Y, std::vector<int> *seeds = nullptr);
+
+// x-slab owned by `rank` of `world` for a grid with X rows (requires X % world == 0 when world > 1)
+void slabOf(int X, int rank, int world, int &a, int &b);
+
+} // namespace detail
+} // namespace ogmaneo

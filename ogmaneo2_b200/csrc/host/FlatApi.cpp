@@ -1,0 +1,268 @@
+// csrc/host/FlatApi.cpp — the flat C ABI (include/ogn_hierarchy_api.h, prefix ogn_) on top of the C++ drop-in classes,
+// plus product-only entry points (include/ogn_b200.h): device-resident stepping, ensembles, sharding, hash init.
+#include <ogmaneo/Hierarchy.h>
+
+#include <cstring>
+#include <fstream>
+#include <string>
+
+#include "../../../include/ogn_b200.h"
+#include "Device.h"
+
+using namespace ogmaneo;
+
+namespace {
+struct Handle {
+    ComputeSystem cs;
+    Hierarchy h;
+    std::vector<InputType> types;
+};
+thread_local std::string g_err;
+
+template <typename F> int guard(F &&f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    } catch (...) {
+        g_err = "unknown error";
+        return 1;
+    }
+}
+template <typename T> int copyOut(const std::vector<T> &v, T *out) {
+    if (out && !v.empty()) std::memcpy(out, v.data(), v.size() * sizeof(T));
+    return (int)v.size();
+}
+
+void unpack(const ogn_hierarchy_desc *d, std::vector<Int3> &sizes, std::vector<InputType> &types, std::vector<Hierarchy::LayerDesc> &lds) {
+    sizes.resize(d->num_inputs); types.resize(d->num_inputs); lds.resize(d->num_layers);
+    for (int i = 0; i < d->num_inputs; i++) {
+        sizes[i] = Int3(d->input_sizes[3 * i], d->input_sizes[3 * i + 1], d->input_sizes[3 * i + 2]);
+        types[i] = (InputType)d->input_types[i];
+    }
+    for (int l = 0; l < d->num_layers; l++) {
+        const ogn_layer_desc &s = d->layers[l];
+        lds[l].hiddenSize = Int3(s.hidden_x, s.hidden_y, s.hidden_z);
+        lds[l].ffRadius = s.ff_radius; lds[l].pRadius = s.p_radius; lds[l].ticksPerUpdate = s.ticks_per_update;
+        lds[l].temporalHorizon = s.temporal_horizon; lds[l].aRadius = s.a_radius; lds[l].historyCapacity = s.history_capacity;
+    }
+}
+int64_t weightsOut(const std::vector<float> &w, float *out, int64_t cap) {
+    if (out && cap > 0) std::memcpy(out, w.data(), (size_t)std::min<int64_t>(cap, (int64_t)w.size()) * sizeof(float));
+    return (int64_t)w.size();
+}
+} // namespace
+
+extern "C" {
+
+const char *ogn_last_error(void) { return g_err.c_str(); }
+int ogn_set_num_threads(int n) { ComputeSystem::setNumThreads(n); return 0; }
+
+int ogn_create_ex(const ogn_hierarchy_desc *d, uint32_t seed, const ogn_create_options *opt, void **out) {
+    *out = nullptr;
+    return guard([&] {
+        std::unique_ptr<Handle> H(new Handle());
+        H->cs.rng.seed(seed);
+        std::vector<Int3> sizes; std::vector<Hierarchy::LayerDesc> lds;
+        unpack(d, sizes, H->types, lds);
+        int ensemble = 1;
+        if (opt) {
+            H->cs.device = opt->device;
+            H->cs.deviceInit = opt->device_init != 0;
+            H->cs.deviceInitSeed = seed;
+            if (opt->replay_rng) H->cs.replayRng = true;
+            H->cs.shardRank = opt->shard_rank; H->cs.shardWorld = opt->shard_world > 0 ? opt->shard_world : 1;
+            H->cs.allGather = opt->all_gather; H->cs.allGatherUser = opt->all_gather_user;
+            ensemble = opt->ensemble > 0 ? opt->ensemble : 1;
+        }
+        if (ensemble > 1 || (opt && opt->ensemble_seeds)) {
+            std::vector<unsigned> seeds(ensemble);
+            for (int k = 0; k < ensemble; k++) seeds[k] = opt->ensemble_seeds ? opt->ensemble_seeds[k] : seed + (unsigned)k;
+            H->h.initRandomEnsemble(H->cs, seeds, sizes, H->types, lds);
+        } else
+            H->h.initRandom(H->cs, sizes, H->types, lds);
+        *out = H.release();
+    });
+}
+int ogn_create(const ogn_hierarchy_desc *d, uint32_t seed, void **out) {
+    ogn_create_options opt;
+    std::memset(&opt, 0, sizeof(opt));
+    opt.device = -1; opt.replay_rng = 1; opt.shard_world = 1; opt.ensemble = 1;
+    return ogn_create_ex(d, seed, &opt, out);
+}
+void ogn_destroy(void *h) {
+    try { delete (Handle *)h; } catch (...) {}
+}
+
+int ogn_step(void *hh, const int *const *input_cs, int learn, float reward, int mimic) {
+    return guard([&] {
+        Handle *H = (Handle *)hh;
+        const std::vector<Int3> &sz = H->h.getInputSizes();
+        const int B = H->h.getEnsembleSize();
+        std::vector<IntBuffer> bufs(sz.size());
+        std::vector<const IntBuffer *> ptrs(sz.size());
+        for (size_t i = 0; i < sz.size(); i++) {
+            bufs[i].assign(input_cs[i], input_cs[i] + (size_t)sz[i].x * sz[i].y * B);
+            ptrs[i] = &bufs[i];
+        }
+        H->h.step(H->cs, ptrs, learn != 0, reward, mimic != 0);
+    });
+}
+int ogn_step_device(void *hh, const int *const *input_cs_dev, int learn, float reward, int mimic) {
+    return guard([&] {
+        Handle *H = (Handle *)hh;
+        std::vector<const int *> ptrs(input_cs_dev, input_cs_dev + H->h.getInputSizes().size());
+        H->h.stepDevice(H->cs, ptrs, learn != 0, reward, mimic != 0);
+    });
+}
+int ogn_synchronize(void *hh) { return guard([&] { ((Handle *)hh)->cs.synchronize(); }); }
+void *ogn_stream(void *hh) {
+    void *s = nullptr;
+    guard([&] { s = ((Handle *)hh)->cs.stream(); });
+    return s;
+}
+const int *ogn_prediction_cs_device(void *hh, int i) {
+    const int *p = nullptr;
+    guard([&] { p = ((Handle *)hh)->h.getPredictionCsDevice(i); });
+    return p;
+}
+int ogn_ensemble_size(void *hh) { return ((Handle *)hh)->h.getEnsembleSize(); }
+uint64_t ogn_take_sc_update_count(void *hh, int l) {
+    uint64_t v = 0;
+    guard([&] { v = ((Handle *)hh)->h.getSCLayer(l).takeUpdateCount(); });
+    return v;
+}
+
+int ogn_num_layers(void *h) { return ((Handle *)h)->h.getNumLayers(); }
+int ogn_get_update(void *h, int l) { return ((Handle *)h)->h.getUpdate(l); }
+int ogn_get_ticks(void *h, int l) { return ((Handle *)h)->h.getTicks(l); }
+int ogn_get_ticks_per_update(void *h, int l) { return ((Handle *)h)->h.getTicksPerUpdate(l); }
+
+int ogn_get_prediction_cs(void *hh, int i, int *out) {
+    int n = -1;
+    guard([&] {
+        Hierarchy &h = ((Handle *)hh)->h;
+        if (h.getALayers()[i] == nullptr && h.getPLayers(0)[i] == nullptr) return;
+        n = copyOut(h.getPredictionCs(i), out);
+    });
+    return n;
+}
+int ogn_sc_hidden_cs(void *h, int l, int *out) {
+    int n = -1;
+    guard([&] { n = copyOut(((Handle *)h)->h.getSCLayer(l).getHiddenCs(), out); });
+    return n;
+}
+int ogn_sc_hidden_cs_prev(void *h, int l, int *out) {
+    int n = -1;
+    guard([&] { n = copyOut(((Handle *)h)->h.getSCLayer(l).getHiddenCsPrev(), out); });
+    return n;
+}
+int ogn_sc_num_visible(void *h, int l) { return ((Handle *)h)->h.getSCLayer(l).getNumVisibleLayers(); }
+int64_t ogn_sc_weights(void *h, int l, int vli, float *out, int64_t cap) {
+    int64_t n = -1;
+    guard([&] {
+        std::vector<float> w;
+        ((Handle *)h)->h.getSCLayer(l).getWeights(vli, w);
+        n = weightsOut(w, out, cap);
+    });
+    return n;
+}
+int ogn_sc_reconstructions(void *h, int l, int vli, float *out) {
+    int n = -1;
+    guard([&] {
+        FloatBuffer r;
+        ((Handle *)h)->h.getSCLayer(l).getReconstructions(vli, r);
+        n = copyOut(r, out);
+    });
+    return n;
+}
+int ogn_pred_count(void *h, int l) { return (int)((Handle *)h)->h.getPLayers(l).size(); }
+int ogn_pred_exists(void *h, int l, int p) { return ((Handle *)h)->h.getPLayers(l)[p] != nullptr; }
+int ogn_pred_hidden_cs(void *h, int l, int p, int *out) {
+    int n = -1;
+    guard([&] { n = copyOut(((Handle *)h)->h.getPLayers(l)[p]->getHiddenCs(), out); });
+    return n;
+}
+int ogn_pred_activations(void *h, int l, int p, float *out) {
+    int n = -1;
+    guard([&] { n = copyOut(((Handle *)h)->h.getPLayers(l)[p]->getHiddenActivations(), out); });
+    return n;
+}
+int ogn_pred_num_visible(void *h, int l, int p) { return ((Handle *)h)->h.getPLayers(l)[p]->getNumVisibleLayers(); }
+int64_t ogn_pred_weights(void *h, int l, int p, int vli, float *out, int64_t cap) {
+    int64_t n = -1;
+    guard([&] {
+        std::vector<float> w;
+        ((Handle *)h)->h.getPLayers(l)[p]->getWeights(vli, w);
+        n = weightsOut(w, out, cap);
+    });
+    return n;
+}
+int ogn_pred_input_cs_prev(void *h, int l, int p, int vli, int *out) {
+    int n = -1;
+    guard([&] { n = copyOut(((Handle *)h)->h.getPLayers(l)[p]->getInputCsPrev(vli), out); });
+    return n;
+}
+int ogn_actor_exists(void *h, int p) { return ((Handle *)h)->h.getALayers()[p] != nullptr; }
+int ogn_actor_hidden_cs(void *h, int p, int *out) {
+    int n = -1;
+    guard([&] { n = copyOut(((Handle *)h)->h.getALayers()[p]->getHiddenCs(), out); });
+    return n;
+}
+int ogn_actor_values(void *h, int p, float *out) {
+    int n = -1;
+    guard([&] { n = copyOut(((Handle *)h)->h.getALayers()[p]->getHiddenValues(), out); });
+    return n;
+}
+int ogn_actor_num_visible(void *h, int p) { return ((Handle *)h)->h.getALayers()[p]->getNumVisibleLayers(); }
+int64_t ogn_actor_weights(void *h, int p, int vli, int which, float *out, int64_t cap) {
+    int64_t n = -1;
+    guard([&] {
+        std::vector<float> w;
+        ((Handle *)h)->h.getALayers()[p]->getWeights(vli, which, w);
+        n = weightsOut(w, out, cap);
+    });
+    return n;
+}
+int ogn_set_sc_alpha(void *h, int l, float a) { ((Handle *)h)->h.getSCLayer(l).alpha = a; return 0; }
+int ogn_set_pred_alpha(void *h, int l, int p, float a) { ((Handle *)h)->h.getPLayers(l)[p]->alpha = a; return 0; }
+int ogn_set_actor_params(void *h, int p, float alpha, float beta, float gamma, int minSteps, int historyIters) {
+    Actor &a = *((Handle *)h)->h.getALayers()[p];
+    a.alpha = alpha; a.beta = beta; a.gamma = gamma; a.minSteps = minSteps; a.historyIters = historyIters;
+    return 0;
+}
+int64_t ogn_save(void *h, const char *path) {
+    int64_t n = -1;
+    guard([&] {
+        std::ofstream os(path, std::ios::binary);
+        if (!os) throw std::runtime_error("cannot open file for writing");
+        ((Handle *)h)->h.writeToStream(os);
+        n = (int64_t)os.tellp();
+    });
+    return n;
+}
+int ogn_load(const char *path, uint32_t seed, void **out) {
+    *out = nullptr;
+    return guard([&] {
+        std::ifstream is(path, std::ios::binary);
+        if (!is) throw std::runtime_error("cannot open file");
+        std::unique_ptr<Handle> H(new Handle());
+        H->cs.rng.seed(seed);
+        H->cs.replayRng = true;
+        H->h.readFromStream(is, H->cs);
+        *out = H.release();
+    });
+}
+uint32_t ogn_rng_peek(void *h) {
+    std::mt19937 c = ((Handle *)h)->cs.rng;
+    return (uint32_t)c();
+}
+int ogn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+} // extern "C"

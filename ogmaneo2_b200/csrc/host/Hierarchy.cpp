@@ -1,0 +1,405 @@
+// csrc/host/Hierarchy.cpp — ogmaneo::Hierarchy: device-resident histories + the tick schedule that sequences the
+// layer kernels on one stream (public interface: include/ogmaneo/Hierarchy.h).
+#include "LayerImpl.h"
+
+#include <cassert>
+
+namespace ogmaneo {
+using namespace detail;
+
+namespace {
+// CircleBuffer<IntBuffer> (Helpers.h:85-139) in HBM: T slots of n ints, logical index 0 = most recent.
+struct Ring {
+    DevBuf<int> buf;
+    int T = 0, start = 0;
+    size_t n = 0;
+    void alloc(int T_, size_t n_, cudaStream_t s) { T = T_; n = n_; start = 0; buf.allocZero((size_t)T * n, s); }
+    void pushFront() { if (--start < 0) start += T; }
+    int *slot(int logical) const { return buf.ptr() + (size_t)((start + logical) % T) * n; }
+    void cloneFrom(const Ring &o, cudaStream_t s) { T = o.T; n = o.n; start = o.start; buf.cloneFrom(o.buf, s); }
+};
+} // namespace
+
+struct Hierarchy::Impl {
+    std::shared_ptr<DeviceContext> ctx;
+    int batch = 1;
+    std::vector<std::vector<Ring>> histories; // [layer][input]
+    std::vector<std::unique_ptr<PinnedBuf<int>>> inPinned;
+    cudaEvent_t inFree = nullptr; // pinned input staging may be overwritten after this event
+    ~Impl() { if (inFree) cudaEventDestroy(inFree); }
+};
+
+Hierarchy::Hierarchy() : impl(nullptr) {}
+Hierarchy::~Hierarchy() { delete impl; }
+Hierarchy::Hierarchy(const Hierarchy &o) : impl(nullptr) { *this = o; }
+
+// Hierarchy.cpp:149-190 (deep copy)
+const Hierarchy &Hierarchy::operator=(const Hierarchy &o) {
+    if (this == &o) return *this;
+    scLayers = o.scLayers;
+    updates = o.updates; ticks = o.ticks; ticksPerUpdate = o.ticksPerUpdate; inputSizes = o.inputSizes;
+    pLayers.clear(); pLayers.resize(o.pLayers.size());
+    for (size_t l = 0; l < o.pLayers.size(); l++) {
+        pLayers[l].resize(o.pLayers[l].size());
+        for (size_t v = 0; v < o.pLayers[l].size(); v++)
+            if (o.pLayers[l][v]) pLayers[l][v].reset(new Predictor(*o.pLayers[l][v]));
+    }
+    aLayers.clear(); aLayers.resize(o.aLayers.size());
+    for (size_t v = 0; v < o.aLayers.size(); v++)
+        if (o.aLayers[v]) aLayers[v].reset(new Actor(*o.aLayers[v]));
+    delete impl; impl = nullptr;
+    if (o.impl) {
+        impl = new Impl();
+        impl->ctx = o.impl->ctx; impl->batch = o.impl->batch;
+        cudaCheck(cudaSetDevice(impl->ctx->device), "cudaSetDevice");
+        impl->histories.resize(o.impl->histories.size());
+        for (size_t l = 0; l < impl->histories.size(); l++) {
+            impl->histories[l].resize(o.impl->histories[l].size());
+            for (size_t i = 0; i < impl->histories[l].size(); i++) impl->histories[l][i].cloneFrom(o.impl->histories[l][i], impl->ctx->stream);
+        }
+        for (size_t i = 0; i < o.impl->inPinned.size(); i++) {
+            impl->inPinned.emplace_back(new PinnedBuf<int>());
+            impl->inPinned.back()->alloc(o.impl->inPinned[i]->size());
+        }
+        cudaCheck(cudaEventCreateWithFlags(&impl->inFree, cudaEventDisableTiming), "cudaEventCreate");
+        cudaCheck(cudaEventRecord(impl->inFree, impl->ctx->stream), "cudaEventRecord");
+        impl->ctx->sync();
+    }
+    return *this;
+}
+
+// Hierarchy.cpp:16-147. The order of the initRandom calls (layer-0 predictors / actors by input index, SparseCoder 0,
+// layer-1 predictors, SparseCoder 1, ...) is the order in which cs.rng is consumed and must not change.
+void Hierarchy::initImpl(ComputeSystem &cs, const std::vector<Int3> &inSizes, const std::vector<InputType> &inTypes,
+                         const std::vector<LayerDesc> &lds, int batch, int member) {
+    const int L = (int)lds.size(), NI = (int)inSizes.size();
+    const bool first = member == 0;
+    if (first) {
+        for (int i = 0; i < NI; i++)
+            if (inTypes[i] == InputType::action) {
+                if (batch > 1) throw std::runtime_error("ogmaneo-b200: ensembles do not support action inputs");
+                cs.replayRng = true; // Actor sampling depends on every earlier draw from cs.rng
+            }
+        delete impl; impl = new Impl();
+        impl->ctx = cs.sharedContext(); impl->batch = batch;
+        scLayers.clear(); scLayers.resize(L);
+        pLayers.clear(); pLayers.resize(L);
+        aLayers.clear();
+        ticks.assign(L, 0); updates.assign(L, 0); ticksPerUpdate.resize(L);
+        inputSizes = inSizes;
+        for (auto &s : inputSizes) s.pad = 0;
+        for (int l = 0; l < L; l++) ticksPerUpdate[l] = l == 0 ? 1 : lds[l].ticksPerUpdate;
+        impl->histories.clear(); impl->histories.resize(L);
+        impl->inPinned.clear();
+        cudaCheck(cudaEventCreateWithFlags(&impl->inFree, cudaEventDisableTiming), "cudaEventCreate");
+        cudaCheck(cudaEventRecord(impl->inFree, impl->ctx->stream), "cudaEventRecord");
+    }
+    cudaStream_t st = impl->ctx->stream;
+    for (int l = 0; l < L; l++) {
+        std::vector<SparseCoder::VisibleLayerDesc> scV;
+        std::vector<Predictor::VisibleLayerDesc> pV(1);
+        pV[0].size = lds[l].hiddenSize; pV[0].radius = lds[l].pRadius;
+        if (l < L - 1) pV.push_back(pV[0]);
+        if (l == 0) {
+            const int T = lds[l].temporalHorizon;
+            scV.resize((size_t)NI * T);
+            for (int i = 0; i < NI; i++)
+                for (int t = 0; t < T; t++) { scV[t + T * i].size = inSizes[i]; scV[t + T * i].radius = lds[l].ffRadius; }
+            std::vector<Actor::VisibleLayerDesc> aV(1);
+            aV[0].size = lds[l].hiddenSize; aV[0].radius = lds[l].aRadius;
+            if (l < L - 1) aV.push_back(aV[0]);
+            if (first) {
+                impl->histories[l].resize(NI);
+                for (int i = 0; i < NI; i++) {
+                    const size_t n = (size_t)inSizes[i].x * inSizes[i].y * batch;
+                    impl->histories[l][i].alloc(T, n, st);
+                    impl->inPinned.emplace_back(new PinnedBuf<int>());
+                    impl->inPinned.back()->alloc(n);
+                }
+                pLayers[l].resize(NI); aLayers.resize(NI);
+            }
+            for (int p = 0; p < NI; p++) {
+                if (inTypes[p] == InputType::prediction) {
+                    if (first) pLayers[l][p].reset(new Predictor());
+                    pLayers[l][p]->initRandomMember(cs, inSizes[p], pV, batch, member);
+                } else if (inTypes[p] == InputType::action) {
+                    aLayers[p].reset(new Actor());
+                    aLayers[p]->initRandom(cs, inSizes[p], lds[l].historyCapacity, aV);
+                }
+            }
+        } else {
+            const int T = lds[l].temporalHorizon;
+            scV.resize(T);
+            for (int t = 0; t < T; t++) { scV[t].size = lds[l - 1].hiddenSize; scV[t].radius = lds[l].ffRadius; }
+            if (first) {
+                impl->histories[l].resize(1);
+                impl->histories[l][0].alloc(T, (size_t)lds[l - 1].hiddenSize.x * lds[l - 1].hiddenSize.y * batch, st);
+                pLayers[l].resize(lds[l].ticksPerUpdate);
+            }
+            for (size_t p = 0; p < pLayers[l].size(); p++) {
+                if (first) pLayers[l][p].reset(new Predictor());
+                pLayers[l][p]->initRandomMember(cs, lds[l - 1].hiddenSize, pV, batch, member);
+            }
+        }
+        scLayers[l].initRandomMember(cs, lds[l].hiddenSize, scV, batch, member);
+    }
+    impl->ctx->sync();
+}
+
+void Hierarchy::initRandom(ComputeSystem &cs, const std::vector<Int3> &inSizes, const std::vector<InputType> &inTypes,
+                           const std::vector<LayerDesc> &lds) {
+    initImpl(cs, inSizes, inTypes, lds, 1, 0);
+}
+
+void Hierarchy::initRandomEnsemble(ComputeSystem &cs, const std::vector<unsigned> &seeds, const std::vector<Int3> &inSizes,
+                                   const std::vector<InputType> &inTypes, const std::vector<LayerDesc> &lds) {
+    if (cs.shardWorld > 1) throw std::runtime_error("ogmaneo-b200: shard an ensemble by giving each device its own members");
+    for (size_t k = 0; k < seeds.size(); k++) {
+        cs.rng.seed(seeds[k]);
+        cs.deviceInitSeed = seeds[k];
+        cs.deviceInitMatrix = 0;
+        initImpl(cs, inSizes, inTypes, lds, (int)seeds.size(), (int)k);
+    }
+}
+
+int Hierarchy::getEnsembleSize() const { return impl ? impl->batch : 0; }
+
+// Hierarchy.cpp:192-285
+void Hierarchy::stepImpl(ComputeSystem &cs, const std::vector<const IntBuffer *> *hostIn, const std::vector<const int *> *devIn,
+                         bool learnEnabled, float reward, bool mimic) {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    const int L = (int)scLayers.size(), NI = (int)inputSizes.size();
+    if ((hostIn ? hostIn->size() : devIn->size()) != (size_t)NI) throw std::invalid_argument("ogmaneo-b200: wrong number of input CSDRs");
+
+    ticks[0] = 0;
+    // K1: inputs -> front of the layer-0 history rings
+    if (hostIn) cudaCheck(cudaEventSynchronize(m.inFree), "cudaEventSynchronize");
+    for (int i = 0; i < NI; i++) {
+        Ring &r = m.histories[0][i];
+        r.pushFront();
+        consumeKernel1(cs, (int)(r.n / m.batch));
+        if (hostIn) {
+            if ((*hostIn)[i]->size() != r.n) throw std::invalid_argument("ogmaneo-b200: input CSDR has the wrong number of columns");
+            std::memcpy(m.inPinned[i]->ptr(), (*hostIn)[i]->data(), r.n * sizeof(int));
+            cudaCheck(cudaMemcpyAsync(r.slot(0), m.inPinned[i]->ptr(), r.n * sizeof(int), cudaMemcpyHostToDevice, ctx.stream), "input H2D");
+        } else
+            cudaCheck(cudaMemcpyAsync(r.slot(0), (*devIn)[i], r.n * sizeof(int), cudaMemcpyDeviceToDevice, ctx.stream), "input D2D");
+    }
+    if (hostIn) cudaCheck(cudaEventRecord(m.inFree, ctx.stream), "cudaEventRecord");
+
+    updates.assign(L, 0);
+    std::vector<const int *> ptrs;
+    // forward (bottom-up) pass of the SparseCoders
+    for (int l = 0; l < L; l++) {
+        if (!(l == 0 || ticks[l] >= ticksPerUpdate[l])) continue;
+        ticks[l] = 0; updates[l] = 1;
+        const size_t NH = m.histories[l].size(), T = (size_t)m.histories[l][0].T;
+        ptrs.resize(NH * T);
+        for (size_t i = 0; i < NH; i++)
+            for (size_t t = 0; t < T; t++) ptrs[t + T * i] = m.histories[l][i].slot((int)t);
+        int *copyOut = nullptr;
+        if (l < L - 1) { // K5: the new hidden state also becomes the next layer's most recent input
+            m.histories[l + 1][0].pushFront();
+            copyOut = m.histories[l + 1][0].slot(0);
+        }
+        scLayers[l].stepDevice(cs, ptrs.data(), learnEnabled, copyOut);
+        if (l < L - 1) {
+            consumeKernel1(cs, scLayers[l].getHiddenSize().x * scLayers[l].getHiddenSize().y);
+            ticks[l + 1]++;
+        }
+    }
+    // backward (top-down) pass of the Predictors / Actors
+    for (int l = L - 1; l >= 0; l--) {
+        if (!updates[l]) continue;
+        const int *fb[2] = {scLayers[l].hiddenCsDevice(), nullptr};
+        if (l < L - 1) fb[1] = pLayers[l + 1][ticksPerUpdate[l + 1] - 1 - ticks[l + 1]]->hiddenCsDevice();
+        for (size_t p = 0; p < pLayers[l].size(); p++) {
+            if (!pLayers[l][p]) continue;
+            const int *target = l == 0 ? m.histories[0][p].slot(0) : m.histories[l][0].slot((int)p);
+            pLayers[l][p]->stepDevice(cs, learnEnabled, target, true, fb);
+        }
+        if (l == 0)
+            for (size_t p = 0; p < aLayers.size(); p++)
+                if (aLayers[p]) aLayers[p]->stepDevice(cs, fb, m.histories[0][p].slot(0), reward, learnEnabled, mimic);
+    }
+}
+
+void Hierarchy::step(ComputeSystem &cs, const std::vector<const IntBuffer *> &inputCs, bool learnEnabled, float reward, bool mimic) {
+    stepImpl(cs, &inputCs, nullptr, learnEnabled, reward, mimic);
+}
+
+void Hierarchy::stepDevice(ComputeSystem &cs, const std::vector<const int *> &inputCsDevice, bool learnEnabled, float reward, bool mimic) {
+    stepImpl(cs, nullptr, &inputCsDevice, learnEnabled, reward, mimic);
+}
+
+const int *Hierarchy::getPredictionCsDevice(int i) const {
+    if (aLayers[i] != nullptr) return aLayers[i]->hiddenCsDevice();
+    return pLayers.front()[i]->hiddenCsDevice();
+}
+
+// --- state ---------------------------------------------------------------------------------------------------------
+namespace {
+void ringToHost(const Ring &r, DeviceContext &ctx, CircleBuffer<IntBuffer> &out) {
+    out.resize(r.T);
+    out.start = r.start;
+    for (int t = 0; t < r.T; t++) { // physical order, so that `start` means the same thing
+        out.data[t].resize(r.n);
+        cudaCheck(cudaMemcpyAsync(out.data[t].data(), r.buf.ptr() + (size_t)t * r.n, r.n * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream), "history D2H");
+    }
+    ctx.sync();
+}
+void ringFromHost(Ring &r, DeviceContext &ctx, const CircleBuffer<IntBuffer> &in) {
+    if (in.size() != r.T) throw std::invalid_argument("ogmaneo-b200: history length mismatch");
+    r.start = in.start;
+    for (int t = 0; t < r.T; t++) {
+        if (in.data[t].size() != r.n) throw std::invalid_argument("ogmaneo-b200: history CSDR size mismatch");
+        cudaCheck(cudaMemcpyAsync(r.buf.ptr() + (size_t)t * r.n, in.data[t].data(), r.n * sizeof(int), cudaMemcpyHostToDevice, ctx.stream), "history H2D");
+    }
+    ctx.sync();
+}
+} // namespace
+
+// Hierarchy.cpp:434-466
+void Hierarchy::getState(State &state) const {
+    const int L = (int)scLayers.size();
+    cudaCheck(cudaSetDevice(impl->ctx->device), "cudaSetDevice");
+    state.hiddenCs.resize(L); state.hiddenCsPrev.resize(L); state.predHiddenCs.resize(L); state.predInputCsPrev.resize(L);
+    state.histories.resize(L);
+    for (int l = 0; l < L; l++) {
+        state.hiddenCs[l] = scLayers[l].getHiddenCs();
+        state.hiddenCsPrev[l] = scLayers[l].getHiddenCsPrev();
+        state.predHiddenCs[l].resize(pLayers[l].size());
+        state.predInputCsPrev[l].resize(pLayers[l].size());
+        for (size_t j = 0; j < pLayers[l].size(); j++) {
+            if (!pLayers[l][j]) continue;
+            state.predHiddenCs[l][j] = pLayers[l][j]->getHiddenCs();
+            state.predInputCsPrev[l][j].resize(pLayers[l][j]->getNumVisibleLayers());
+            for (int v = 0; v < pLayers[l][j]->getNumVisibleLayers(); v++) state.predInputCsPrev[l][j][v] = pLayers[l][j]->getInputCsPrev(v);
+        }
+        state.histories[l].resize(impl->histories[l].size());
+        for (size_t i = 0; i < impl->histories[l].size(); i++) ringToHost(impl->histories[l][i], *impl->ctx, state.histories[l][i]);
+    }
+    state.ticks = ticks;
+    state.updates = updates;
+}
+
+// Hierarchy.cpp:468-493
+void Hierarchy::setState(const State &state) {
+    const int L = (int)scLayers.size();
+    cudaCheck(cudaSetDevice(impl->ctx->device), "cudaSetDevice");
+    for (int l = 0; l < L; l++) {
+        scLayers[l].setHiddenState(state.hiddenCs[l], state.hiddenCsPrev[l]);
+        for (size_t i = 0; i < impl->histories[l].size(); i++) ringFromHost(impl->histories[l][i], *impl->ctx, state.histories[l][i]);
+        for (size_t j = 0; j < pLayers[l].size(); j++)
+            if (pLayers[l][j]) pLayers[l][j]->setState(state.predHiddenCs[l][j], state.predInputCsPrev[l][j]);
+    }
+    ticks = state.ticks;
+    updates = state.updates;
+}
+
+// --- streams: Hierarchy.cpp:287-432, layout in SURVEY.md Appendix B --------------------------------------------------
+void Hierarchy::writeToStream(std::ostream &os) const {
+    if (impl->batch > 1) throw std::runtime_error("ogmaneo-b200: writeToStream needs a single hierarchy (not an ensemble)");
+    cudaCheck(cudaSetDevice(impl->ctx->device), "cudaSetDevice");
+    const int L = (int)scLayers.size(), NI = (int)inputSizes.size();
+    os.write(reinterpret_cast<const char *>(&L), sizeof(int));
+    os.write(reinterpret_cast<const char *>(&NI), sizeof(int));
+    os.write(reinterpret_cast<const char *>(inputSizes.data()), NI * sizeof(Int3));
+    os.write(reinterpret_cast<const char *>(updates.data()), L * sizeof(char));
+    os.write(reinterpret_cast<const char *>(ticks.data()), L * sizeof(int));
+    os.write(reinterpret_cast<const char *>(ticksPerUpdate.data()), L * sizeof(int));
+    for (int l = 0; l < L; l++) {
+        int nh = (int)impl->histories[l].size();
+        os.write(reinterpret_cast<const char *>(&nh), sizeof(int));
+        for (int i = 0; i < nh; i++) {
+            CircleBuffer<IntBuffer> h;
+            ringToHost(impl->histories[l][i], *impl->ctx, h);
+            int size = h.size(), start = h.start;
+            os.write(reinterpret_cast<const char *>(&size), sizeof(int));
+            os.write(reinterpret_cast<const char *>(&start), sizeof(int));
+            for (int t = 0; t < size; t++) writeBufferToStream(os, &h[t]); // logical order
+        }
+        scLayers[l].writeToStream(os);
+        for (size_t v = 0; v < pLayers[l].size(); v++) {
+            char exists = pLayers[l][v] != nullptr;
+            os.write(&exists, 1);
+            if (exists) pLayers[l][v]->writeToStream(os);
+        }
+    }
+    for (size_t v = 0; v < aLayers.size(); v++) {
+        char exists = aLayers[v] != nullptr;
+        os.write(&exists, 1);
+        if (exists) aLayers[v]->writeToStream(os);
+    }
+}
+
+void Hierarchy::readFromStream(std::istream &is, ComputeSystem &cs) {
+    int L = 0, NI = 0;
+    is.read(reinterpret_cast<char *>(&L), sizeof(int));
+    is.read(reinterpret_cast<char *>(&NI), sizeof(int));
+    inputSizes.resize(NI);
+    is.read(reinterpret_cast<char *>(inputSizes.data()), NI * sizeof(Int3));
+    for (auto &s : inputSizes) s.pad = 0;
+    scLayers.clear(); scLayers.resize(L);
+    pLayers.clear(); pLayers.resize(L);
+    ticks.resize(L); ticksPerUpdate.resize(L); updates.resize(L);
+    is.read(reinterpret_cast<char *>(updates.data()), L * sizeof(char));
+    is.read(reinterpret_cast<char *>(ticks.data()), L * sizeof(int));
+    is.read(reinterpret_cast<char *>(ticksPerUpdate.data()), L * sizeof(int));
+    delete impl; impl = new Impl();
+    impl->ctx = cs.sharedContext(); impl->batch = 1;
+    cudaCheck(cudaEventCreateWithFlags(&impl->inFree, cudaEventDisableTiming), "cudaEventCreate");
+    cudaCheck(cudaEventRecord(impl->inFree, impl->ctx->stream), "cudaEventRecord");
+    impl->histories.resize(L);
+    for (int l = 0; l < L; l++) {
+        int nh = 0;
+        is.read(reinterpret_cast<char *>(&nh), sizeof(int));
+        impl->histories[l].resize(nh);
+        for (int i = 0; i < nh; i++) {
+            int size = 0, start = 0;
+            is.read(reinterpret_cast<char *>(&size), sizeof(int));
+            is.read(reinterpret_cast<char *>(&start), sizeof(int));
+            CircleBuffer<IntBuffer> h;
+            h.resize(size);
+            h.start = start;
+            for (int t = 0; t < size; t++) readBufferFromStream(is, &h[t]);
+            impl->histories[l][i].alloc(size, size > 0 ? h.data[0].size() : 0, impl->ctx->stream);
+            ringFromHost(impl->histories[l][i], *impl->ctx, h);
+        }
+        scLayers[l].readFromStream(is, cs);
+        pLayers[l].resize(l == 0 ? NI : ticksPerUpdate[l]);
+        for (size_t v = 0; v < pLayers[l].size(); v++) {
+            char exists = 0;
+            is.read(&exists, 1);
+            if (exists) {
+                pLayers[l][v].reset(new Predictor());
+                pLayers[l][v]->readFromStream(is, cs);
+            }
+        }
+    }
+    aLayers.clear(); aLayers.resize(NI);
+    for (int v = 0; v < NI; v++) {
+        char exists = 0;
+        is.read(&exists, 1);
+        if (exists) {
+            aLayers[v].reset(new Actor());
+            aLayers[v]->readFromStream(is, cs);
+            cs.replayRng = true;
+        }
+    }
+    impl->inPinned.clear();
+    for (int i = 0; i < NI; i++) {
+        impl->inPinned.emplace_back(new PinnedBuf<int>());
+        impl->inPinned.back()->alloc((size_t)inputSizes[i].x * inputSizes[i].y);
+    }
+}
+
+void Hierarchy::readFromStream(std::istream &is) {
+    ComputeSystem cs;
+    if (impl) cs.device = impl->ctx->device;
+    readFromStream(is, cs);
+}
+
+} // namespace ogmaneo

@@ -1,0 +1,238 @@
+// csrc/host/SparseCoder.cpp — ogmaneo::SparseCoder on the device (public interface: include/ogmaneo/SparseCoder.h).
+#include "LayerImpl.h"
+
+namespace ogmaneo {
+using namespace detail;
+
+SparseCoder::SparseCoder() : alpha(0.1f), impl(nullptr) {}
+SparseCoder::~SparseCoder() { delete impl; }
+SparseCoder::SparseCoder(const SparseCoder &o) : alpha(0.1f), impl(nullptr) { *this = o; }
+
+SparseCoder &SparseCoder::operator=(const SparseCoder &o) {
+    if (this == &o) return *this;
+    alpha = o.alpha; hiddenSize = o.hiddenSize; visibleLayerDescs = o.visibleLayerDescs;
+    hiddenCs = o.hiddenCs; hiddenCsPrev = o.hiddenCsPrev; visibleLayers = o.visibleLayers;
+    delete impl; impl = nullptr;
+    if (o.impl) {
+        impl = new Impl();
+        DeviceContext &ctx = *o.impl->ctx;
+        cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+        impl->ctx = o.impl->ctx; impl->batch = o.impl->batch; impl->x0 = o.impl->x0; impl->x1 = o.impl->x1;
+        impl->world = o.impl->world; impl->cur = o.impl->cur; impl->prevAliasesCur = o.impl->prevAliasesCur;
+        impl->csDirty = o.impl->csDirty; impl->wDirty = o.impl->wDirty; impl->reconDirty = o.impl->reconDirty;
+        impl->ws.cloneFrom(ctx, o.impl->ws);
+        impl->cs_[0].cloneFrom(o.impl->cs_[0], ctx.stream); impl->cs_[1].cloneFrom(o.impl->cs_[1], ctx.stream);
+        impl->upd.allocZero(1, ctx.stream);
+        impl->inStage.resize(o.impl->inStage.size());
+        ctx.sync();
+    }
+    return *this;
+}
+
+void SparseCoder::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, const std::vector<VisibleLayerDesc> &vlds, int batch_) {
+    ctx = cs.sharedContext();
+    batch = batch_; world = cs.shardWorld;
+    slabOf(hidden.x, cs.shardRank, cs.shardWorld, x0, x1);
+    ws.sets.clear(); ws.sets.resize(vlds.size());
+    for (size_t v = 0; v < vlds.size(); v++)
+        ws.sets[v].allocate(*ctx, Geometry::get(hidden, vlds[v].size, vlds[v].radius), batch, true, true, x0, x1);
+    ws.commit(*ctx);
+    const size_t ncols = (size_t)hidden.x * hidden.y * batch;
+    cs_[0].allocZero(ncols, ctx->stream); cs_[1].allocZero(ncols, ctx->stream);
+    upd.allocZero(1, ctx->stream);
+    inStage.clear(); inStage.resize(vlds.size());
+    cur = 0; prevAliasesCur = true;
+    csDirty = true; reconDirty = true; wDirty.assign(vlds.size(), 1);
+}
+
+// SparseCoder.cpp:85-125
+void SparseCoder::initRandom(ComputeSystem &cs, const Int3 &hiddenSize_, const std::vector<VisibleLayerDesc> &vlds) {
+    initRandomMember(cs, hiddenSize_, vlds, 1, 0);
+}
+
+void SparseCoder::initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize_, const std::vector<VisibleLayerDesc> &vlds, int batch,
+                                   int member) {
+    if (member == 0) {
+        hiddenSize = hiddenSize_; visibleLayerDescs = vlds;
+        visibleLayers.clear(); visibleLayers.resize(vlds.size());
+        delete impl; impl = new Impl();
+        impl->allocate(cs, hiddenSize, vlds, batch);
+    }
+    for (size_t v = 0; v < vlds.size(); v++)
+        impl->ws.sets[v].initialise(*impl->ctx, member, WeightInit{&cs, -1.0f, 0.0f, cs.deviceInitMatrix++});
+}
+
+// SparseCoder.cpp:127-147 with device-resident inputs. copyOut (optional) receives hiddenCs too (next layer's history).
+void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bool learnEnabled, int *copyOut) {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    const int nvl = (int)visibleLayerDescs.size();
+    if (nvl > OGN_MAX_VL) throw std::runtime_error("ogmaneo-b200: more than 32 visible layers on one SparseCoder");
+    ogn_cs_args args;
+    std::memset(&args, 0, sizeof(args));
+    for (int v = 0; v < nvl; v++) args.cs[v] = inputCsDev[v];
+
+    const int outIdx = m.prevAliasesCur ? 1 - m.cur : m.cur;
+    int *out = m.cs_[outIdx].ptr();
+    const int *prev = m.cs_[m.prevAliasesCur ? m.cur : 1 - m.cur].ptr();
+    const bool sharded = m.world > 1;
+
+    consumeKernel2(cs, hiddenSize.x, hiddenSize.y);
+    kernelCheck(ogn_sc_forward(m.ws.devPtr(), nvl, &args, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, out,
+                               sharded ? nullptr : copyOut, ctx.stream), "sc_forward");
+    if (sharded) {
+        if (!cs.allGather) throw std::runtime_error("ogmaneo-b200: shardWorld > 1 needs ComputeSystem::allGather");
+        cs.allGather(cs.allGatherUser, out, (m.x1 - m.x0) * hiddenSize.y, (void *)ctx.stream);
+        if (copyOut)
+            cudaCheck(cudaMemcpyAsync(copyOut, out, (size_t)hiddenSize.x * hiddenSize.y * sizeof(int), cudaMemcpyDeviceToDevice,
+                                      ctx.stream), "hiddenCs D2D");
+    }
+    if (learnEnabled) {
+        int v = 0;
+        while (v < nvl) { // one launch per run of visible layers with the same shape and radius
+            int e = v + 1;
+            while (e < nvl && m.ws.sets[e].geo == m.ws.sets[v].geo) e++;
+            for (int k = v; k < e; k++) consumeKernel2(cs, visibleLayerDescs[k].size.x, visibleLayerDescs[k].size.y);
+            const WeightSet &w = m.ws.sets[v];
+            kernelCheck(ogn_sc_learn(m.ws.devPtr(), v, e - v, &args, out, prev, hiddenSize.x, hiddenSize.y, hiddenSize.z, w.geo->Vx,
+                                     w.geo->Vy, w.geo->Vz, w.vx0, w.vx1, alpha, m.batch, m.upd.ptr(), ctx.stream), "sc_learn");
+            v = e;
+        }
+        std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
+        m.reconDirty = true;
+    }
+    consumeKernel1(cs, hiddenSize.x * hiddenSize.y);
+    m.cur = outIdx; m.prevAliasesCur = true; // hiddenCsPrev := hiddenCs without a copy
+    m.csDirty = true;
+}
+
+void SparseCoder::step(ComputeSystem &cs, const std::vector<const IntBuffer *> &inputCs, bool learnEnabled) {
+    Impl &m = *impl;
+    cudaCheck(cudaSetDevice(m.ctx->device), "cudaSetDevice");
+    std::vector<const int *> ptrs(inputCs.size());
+    for (size_t v = 0; v < inputCs.size(); v++) {
+        if (m.inStage[v].size() != inputCs[v]->size()) m.inStage[v].alloc(inputCs[v]->size());
+        m.inStage[v].upload(inputCs[v]->data(), inputCs[v]->size(), m.ctx->stream);
+        ptrs[v] = m.inStage[v].ptr();
+    }
+    stepDevice(cs, ptrs.data(), learnEnabled, nullptr);
+    m.ctx->sync(); // the caller's buffers were pageable: make the H2D copies complete before returning
+}
+
+// --- host mirrors ------------------------------------------------------------------------------------------------
+void SparseCoder::Impl::refreshCs(IntBuffer &hc, IntBuffer &hcPrev) {
+    if (!csDirty) return;
+    cudaCheck(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t n = cs_[0].size();
+    hc.resize(n); hcPrev.resize(n);
+    cs_[cur].download(hc.data(), n, ctx->stream);
+    cs_[prevAliasesCur ? cur : 1 - cur].download(hcPrev.data(), n, ctx->stream);
+    ctx->sync();
+    csDirty = false;
+}
+
+const IntBuffer &SparseCoder::getHiddenCs() const { impl->refreshCs(hiddenCs, hiddenCsPrev); return hiddenCs; }
+const IntBuffer &SparseCoder::getHiddenCsPrev() const { impl->refreshCs(hiddenCs, hiddenCsPrev); return hiddenCsPrev; }
+
+void SparseCoder::getWeights(int i, std::vector<float> &out) const {
+    cudaCheck(cudaSetDevice(impl->ctx->device), "cudaSetDevice");
+    const WeightSet &w = impl->ws.sets[i];
+    out.assign((size_t)w.geo->nnz, 0.0f);
+    w.downloadCSR(*impl->ctx, 0, out.data());
+}
+
+void SparseCoder::getReconstructions(int i, FloatBuffer &out) const {
+    cudaCheck(cudaSetDevice(impl->ctx->device), "cudaSetDevice");
+    const WeightSet &w = impl->ws.sets[i];
+    out.resize(w.recon.size());
+    w.recon.download(out.data(), out.size(), impl->ctx->stream);
+    impl->ctx->sync();
+}
+
+const SparseCoder::VisibleLayer &SparseCoder::getVisibleLayer(int i) const {
+    VisibleLayer &vl = visibleLayers[i];
+    if (impl->wDirty[i]) {
+        if (vl.weights.rowRanges.empty()) { // pattern once, values every time they changed
+            initSMLocalRF(visibleLayerDescs[i].size, hiddenSize, visibleLayerDescs[i].radius, vl.weights);
+            vl.weights.initT();
+        }
+        getWeights(i, vl.weights.nonZeroValues);
+        impl->wDirty[i] = 0;
+    }
+    if (impl->reconDirty) {
+        for (size_t v = 0; v < visibleLayers.size(); v++) getReconstructions((int)v, visibleLayers[v].reconstructions);
+        impl->reconDirty = false;
+    }
+    return vl;
+}
+
+unsigned long long SparseCoder::takeUpdateCount() {
+    cudaCheck(cudaSetDevice(impl->ctx->device), "cudaSetDevice");
+    unsigned long long v = 0;
+    impl->upd.download(&v, 1, impl->ctx->stream);
+    cudaCheck(cudaMemsetAsync(impl->upd.ptr(), 0, sizeof(v), impl->ctx->stream), "memset");
+    impl->ctx->sync();
+    return v;
+}
+
+// --- streams: SparseCoder.cpp:149-203, layout in SURVEY.md Appendix B ------------------------------------------------
+void SparseCoder::writeToStream(std::ostream &os) const {
+    if (impl->world > 1 || impl->batch > 1) throw std::runtime_error("ogmaneo-b200: writeToStream needs an unsharded single hierarchy");
+    os.write(reinterpret_cast<const char *>(&hiddenSize), sizeof(Int3));
+    os.write(reinterpret_cast<const char *>(&alpha), sizeof(float));
+    writeBufferToStream(os, &getHiddenCs());
+    writeBufferToStream(os, &getHiddenCsPrev());
+    int n = (int)visibleLayerDescs.size();
+    os.write(reinterpret_cast<const char *>(&n), sizeof(int));
+    for (int v = 0; v < n; v++) {
+        os.write(reinterpret_cast<const char *>(&visibleLayerDescs[v]), sizeof(VisibleLayerDesc));
+        writeSMToStream(os, getVisibleLayer(v).weights);
+    }
+}
+
+void SparseCoder::readFromStream(std::istream &is, ComputeSystem &cs) {
+    is.read(reinterpret_cast<char *>(&hiddenSize), sizeof(Int3));
+    hiddenSize.pad = 0;
+    is.read(reinterpret_cast<char *>(&alpha), sizeof(float));
+    IntBuffer hc, hcPrev;
+    readBufferFromStream(is, &hc);
+    readBufferFromStream(is, &hcPrev);
+    int n = 0;
+    is.read(reinterpret_cast<char *>(&n), sizeof(int));
+    visibleLayerDescs.resize(n);
+    std::vector<SparseMatrix> mats(n);
+    for (int v = 0; v < n; v++) {
+        is.read(reinterpret_cast<char *>(&visibleLayerDescs[v]), sizeof(VisibleLayerDesc));
+        visibleLayerDescs[v].size.pad = 0;
+        readSMFromStream(is, mats[v]);
+    }
+    visibleLayers.clear(); visibleLayers.resize(n);
+    delete impl; impl = new Impl();
+    impl->allocate(cs, hiddenSize, visibleLayerDescs, 1);
+    for (int v = 0; v < n; v++) {
+        if ((int64_t)mats[v].nonZeroValues.size() != impl->ws.sets[v].geo->nnz)
+            throw std::runtime_error("ogmaneo-b200: SparseCoder weight count in stream does not match its geometry");
+        impl->ws.sets[v].uploadCSR(*impl->ctx, 0, mats[v].nonZeroValues.data());
+    }
+    setHiddenState(hc, hcPrev);
+}
+
+void SparseCoder::readFromStream(std::istream &is) {
+    ComputeSystem cs; // default device
+    if (impl) cs.device = impl->ctx->device;
+    readFromStream(is, cs);
+}
+
+void SparseCoder::setHiddenState(const IntBuffer &hc, const IntBuffer &hcPrev) {
+    Impl &m = *impl;
+    cudaCheck(cudaSetDevice(m.ctx->device), "cudaSetDevice");
+    m.cs_[0].upload(hc.data(), hc.size(), m.ctx->stream);
+    m.cs_[1].upload(hcPrev.data(), hcPrev.size(), m.ctx->stream);
+    m.ctx->sync();
+    m.cur = 0; m.prevAliasesCur = false;
+    hiddenCs = hc; hiddenCsPrev = hcPrev; m.csDirty = false;
+}
+
+const int *SparseCoder::hiddenCsDevice() const { return impl->cs_[impl->cur].ptr(); }
+
+} // namespace ogmaneo

@@ -21,11 +21,28 @@ REF_SRC = os.environ.get("OGN_REF_DIR", "/root/reference")
 _cache = {}
 
 
+def _digest(sources):
+    import hashlib
+    h = hashlib.sha256()
+    for s in sources:
+        if os.path.exists(s):
+            with open(s, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale(target, sources):
-    if not os.path.exists(target):
+    """Content-hash staleness (mtimes do not survive the snapshot that travels to the GPU box)."""
+    stamp = target + ".sha"
+    if not os.path.exists(target) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.exists(s) and os.path.getmtime(s) > t for s in sources)
+    with open(stamp) as f:
+        return f.read().strip() != _digest(sources)
+
+
+def _stamp(target, sources):
+    with open(target + ".sha", "w") as f:
+        f.write(_digest(sources))
 
 
 def build(verbose=False):
@@ -33,10 +50,13 @@ def build(verbose=False):
     out = None if verbose else subprocess.DEVNULL
     srcs = [os.path.join(HERE, "sph_oracle.cpp"), os.path.join(HERE, "..", "include", "ogn_hierarchy_api.h")]
     if _stale(PORT_SO, srcs):
-        subprocess.check_call(["make", "-C", HERE, "port"], stdout=out)
+        subprocess.check_call(["make", "-B", "-C", HERE, "port"], stdout=out)
+        _stamp(PORT_SO, srcs)
     if os.path.isdir(os.path.join(REF_SRC, "source", "ogmaneo")):
-        if _stale(REF_SO, [os.path.join(HERE, "ref_shim.cpp"), srcs[1]]):
+        rsrcs = [os.path.join(HERE, "ref_shim.cpp"), srcs[1]]
+        if _stale(REF_SO, rsrcs):
             subprocess.check_call(["make", "-C", HERE, "ref", f"REF={REF_SRC}"], stdout=out)
+            _stamp(REF_SO, rsrcs)
 
 
 def port() -> FlatLib:

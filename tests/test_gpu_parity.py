@@ -1,0 +1,72 @@
+"""-m gpu: the CUDA path (through the C ABI of libogn_b200.so) against the CPU checker on the same seeded inputs.
+Bar: every CSDR, activation, weight and the ComputeSystem RNG state bit-identical (integer work and, thanks to the
+order-preserving sums and the glibc expf/tanhf replay, the fp32 work too — so the 1e-5 tolerance north_star allows is
+not needed)."""
+import numpy as np
+import pytest
+
+from ogmaneo2_b200 import configs
+from ogmaneo2_b200.flat_api import InputType, LayerDesc
+
+from common import maker, run_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(product, oracle, cfg, steps, **kw):
+    flat, kind = oracle
+    flat.set_num_threads(1)  # the reference races on cs.rng with more threads and we compare its state
+    err = run_pair(cfg, steps, maker(product.lib()), maker(flat), compare_rng=True, **kw)
+    assert err is None, f"[checker={kind}] {err}"
+
+
+def test_c1_sine(product, oracle):
+    _check(product, oracle, configs.c1_sine(), 400)
+
+
+def test_c2_video_small(product, oracle):
+    _check(product, oracle, configs.c2_video(12, 3), 60)
+
+
+def test_c3_actor(product, oracle):
+    _check(product, oracle, configs.c3_actor(8), 300)
+
+
+def test_c4_large_layer_small(product, oracle):
+    _check(product, oracle, configs.c4_large(24), 30)
+
+
+def test_c5_unit(product, oracle):
+    _check(product, oracle, configs.c5_unit(16), 40, check_every=5)
+
+
+@pytest.mark.parametrize("shape", [
+    dict(inp=(5, 7, 6), hid=(3, 4, 5), r=1),      # downsampling, non-square, Z not a power of two
+    dict(inp=(2, 3, 4), hid=(6, 5, 8), r=2),      # upsampling: fields overlap and clamp everywhere
+    dict(inp=(9, 4, 3), hid=(4, 9, 33), r=3),     # hidden Z > 32 (two lane chunks), radius larger than the grid
+    dict(inp=(6, 6, 40), hid=(5, 5, 7), r=1),     # visible Z > 32
+])
+def test_odd_geometries(product, oracle, shape):
+    cfg = dict(name=f"odd{shape}", inputSizes=[shape["inp"]], inputTypes=[InputType.prediction],
+               layerDescs=[LayerDesc(hiddenSize=shape["hid"], ffRadius=shape["r"], pRadius=shape["r"], temporalHorizon=2),
+                           LayerDesc(hiddenSize=shape["hid"], ffRadius=shape["r"], pRadius=shape["r"], temporalHorizon=2)],
+               streams=["iid"], seed=99)
+    _check(product, oracle, cfg, 40)
+
+
+def test_learning_disabled_and_params(product, oracle):
+    """learnEnabled=False steps interleaved with learning steps, non-default alpha."""
+    flat, kind = oracle
+    cfg = configs.c2_video(8, 2)
+    from common import make_inputs, diff_snapshots
+    a, b = maker(product.lib())(cfg), maker(flat)(cfg)
+    for h in (a, b):
+        h.setSCAlpha(0, 0.25)
+        h.setPredAlpha(0, 0, 0.125)
+    for t in range(30):
+        ins = make_inputs(cfg, t)
+        learn = (t % 3) != 1
+        a.step(ins, learn)
+        b.step(ins, learn)
+    d = diff_snapshots(a.snapshot(True), b.snapshot(True))
+    assert not d, f"[checker={kind}] {d[:3]}"
