@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — hierarchy steps/s (learning on) of the B200 path, its HBM roofline, and the reference CPU path beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c1|c3|c5] [--impl reference]
+
+One JSON line on stdout (rank 0). A "step" is one Hierarchy::step with learning on over one synthetic input CSDR.
+  value   whole-job steps/s with the inputs already resident in HBM (ogn_step_device, CUDA events on the launch stream)
+  e2e     the same through the public host API: Hierarchy.step(host CSDR) + getPredictionCs() every step, i.e. the H2D
+          copy of the input from pinned memory and the D2H read of the prediction are inside the timed region
+  roofline  dominant kernel: algorithmic bytes per launch (SURVEY.md §8d formulas) / its mean launch time measured with
+          CUDA events inside the timed region, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref when it was compiled, else the oracle port) timed on
+          this box's host cores on a bounded sample of the same workload
+
+Default workload: BASELINE config 4 (the large-layer config north_star's target is stated on): 512x512x16 input ->
+one layer of 512x512x32 hidden columns, radius 4, temporalHorizon 1, 2%-noisy drifting stream. With --gpus N > 1
+(launched under torch.distributed.run, one rank per GPU) the same layer is sharded by hidden-column x-slab across the N
+GPUs (strong scaling); the only exchange is an all-gather of int32 CSDR slabs over NCCL after the SparseCoder and after
+the Predictor. PyTorch is used for plumbing only (events on the library's stream, NCCL, process group).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from ogmaneo2_b200 import configs, streams  # noqa: E402
+from ogmaneo2_b200.flat_api import FlatHierarchy, InputType  # noqa: E402
+
+METRIC = "hierarchy_steps_per_s_learn_on"
+UNIT = "steps/s"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# workloads
+def workload(name, n_gpus, size=None):
+    if name == "c4":
+        n = size or 512
+        cfg = configs.c4_large(n)
+        cfg["desc"] = f"C4: {n}x{n}x16 input CSDR -> 1 layer {n}x{n}x32 hidden columns, r=4, temporalHorizon=1, noisy(2%) stream"
+        cfg["sample"] = configs.c4_large(64)
+        cfg["device_init"] = True  # 2.2e10 weights: the reference cannot even construct this size
+    elif name == "c2":
+        cfg = configs.c2_video(32, 3)
+        cfg["desc"] = "C2: 32x32x16 input CSDR -> 3 layers 32x32x32, r=3, prediction on every layer, noisy(2%) stream"
+        cfg["sample"] = configs.c2_video(32, 3)
+        cfg["device_init"] = False
+    elif name == "c1":
+        cfg = configs.c1_sine()
+        cfg["desc"] = "C1: sine 1x1x32 -> 4 layers 4x4x16, r=2"
+        cfg["sample"] = configs.c1_sine()
+        cfg["device_init"] = False
+    elif name == "c3":
+        cfg = configs.c3_actor(8)
+        cfg["desc"] = "C3: 8x8x16 observation + 2x2x4 action -> 3 layers 8x8x16, Actor head"
+        cfg["sample"] = configs.c3_actor(8)
+        cfg["device_init"] = False
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    cfg["key"] = name
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# algorithmic bytes: pairs P of a receptive-field geometry and per-kernel-kind bytes per step
+def rf_pairs(hidden, visible, r):
+    def axis(H, V):
+        s = np.float32(V) / np.float32(H)
+        tot = 0
+        for o in range(H):
+            c = int(np.float32(o) * s + np.float32(0.5))
+            tot += max(0, min(V - 1, c + r) - max(0, c - r) + 1)
+        return tot
+    return axis(hidden[0], visible[0]) * axis(hidden[1], visible[1])
+
+
+def bytes_per_launch(cfg):
+    """[(layer, kind, bytes per launch excluding the data-dependent SC writes, bytes per updated pair)] per launch site."""
+    L = len(cfg["layerDescs"])
+    sites = []
+    for l, ld in enumerate(cfg["layerDescs"]):
+        H = ld.hiddenSize
+        if l == 0:
+            vis = [s for s in cfg["inputSizes"] for _ in range(ld.temporalHorizon)]
+        else:
+            vis = [cfg["layerDescs"][l - 1].hiddenSize] * ld.temporalHorizon
+        fwd = sum(4 * rf_pairs(H, v, ld.ffRadius) * H[2] for v in vis)
+        rec = sum(4 * rf_pairs(H, v, ld.ffRadius) * v[2] for v in vis)
+        sites.append((l, "sc_forward", fwd, 0))
+        sites.append((l, "sc_learn", rec, 4 * vis[0][2]))
+        nvl = 2 if l < L - 1 else 1
+        if l == 0:
+            preds = [s for s, t in zip(cfg["inputSizes"], cfg["inputTypes"]) if t == InputType.prediction]
+        else:
+            preds = [cfg["layerDescs"][l - 1].hiddenSize] * ld.ticksPerUpdate
+        for ph in preds:
+            sites.append((l, "pred_step", 12 * rf_pairs(ph, H, ld.pRadius) * ph[2] * nvl, 0))
+    return sites
+
+
+def tick_counts(cfg, steps):
+    """how many times each layer updates in `steps` steps from a fresh hierarchy (Hierarchy.cpp:219-249)"""
+    L = len(cfg["layerDescs"])
+    tpu = [1] + [ld.ticksPerUpdate for ld in cfg["layerDescs"][1:]]
+    ticks = [0] * L
+    counts = np.zeros((steps, L), dtype=np.int64)
+    for s in range(steps):
+        ticks[0] = 0
+        for l in range(L):
+            if l == 0 or ticks[l] >= tpu[l]:
+                ticks[l] = 0
+                counts[s, l] = 1
+                if l < L - 1:
+                    ticks[l + 1] += 1
+    return counts
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        mhz, mx, reasons, power = [], None, set(), []
+        for ts, line in self.rows:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    mhz.append(float(p[0]))
+                    power.append(float(p[2]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active") and t0 - 0.05 <= ts <= t1 + 0.15:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(mhz)}
+
+
+class _DevArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def time_cpu(cfg_sample, steps, warmup, full_cols, budget_s=25.0):
+    """The reference's CPU implementation on a bounded sample; returns (full-workload steps/s, info dict)."""
+    from oracle import loader
+    flat, kind = loader.best()
+    cores = os.cpu_count() or 1
+    has_actor = any(t == InputType.action for t in cfg_sample["inputTypes"])
+    threads = 1 if has_actor else cores  # the reference's Actor path is only deterministic single-threaded
+    flat.set_num_threads(threads)
+    t0 = time.perf_counter()
+    h = FlatHierarchy(flat, cfg_sample["inputSizes"], cfg_sample["inputTypes"], cfg_sample["layerDescs"], cfg_sample["seed"])
+    t_init = time.perf_counter() - t0
+    ins = lambda t: [streams.make(k if k != "action" else "iid", t, s) for s, k in zip(cfg_sample["inputSizes"], cfg_sample["streams"])]
+    for t in range(warmup):
+        h.step(ins(t), True)
+    done, t0 = 0, time.perf_counter()
+    pre = [ins(warmup + t) for t in range(steps)]
+    t0 = time.perf_counter()
+    for t in range(steps):
+        h.step(pre[t], True)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    sample_cols = sum(ld.hiddenSize[0] * ld.hiddenSize[1] for ld in cfg_sample["layerDescs"][:1])
+    sample_sps = done / dt
+    scale = sample_cols / full_cols  # column-steps/s is the size-independent rate for the single-layer config
+    h.close()
+    info = {"kind": kind, "cores": threads, "sample": f"{cfg_sample['name']}: {done} steps in {dt:.2f}s after {warmup} warm-up "
+            f"(init {t_init:.1f}s), scaled by hidden columns {sample_cols}/{full_cols}", "sample_steps_per_s": sample_sps}
+    return sample_sps * scale, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--stream", default="noisy", help="input stream kind for prediction inputs: noisy|coherent|iid")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--size", type=int, default=None, help="c4 only: grid edge (default 512); smaller sizes are for profiling runs")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = workload(args.workload, args.gpus, args.size)
+    full_cols = cfg["layerDescs"][0].hiddenSize[0] * cfg["layerDescs"][0].hiddenSize[1]
+    config = {"workload": cfg["desc"], "stream": args.stream, "weights": "fp32, random init", "learn": True}
+
+    # ------------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        K = args.steps if args.steps is not None else 10
+        W = args.warmup if args.warmup is not None else 3
+        value, info = time_cpu(cfg["sample"], K, W, full_cols, budget_s=120.0)
+        info["value"] = value
+        info["unit"] = UNIT
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+                          "warmup": W, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": info,
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------------------------------------ B200 arm
+    K = args.steps if args.steps is not None else (200 if args.workload == "c4" else 2000)
+    W = args.warmup if args.warmup is not None else (20 if args.workload == "c4" else 200)
+    W = max(W, 3)
+    import torch
+    import ogmaneo2_b200 as og
+    from ogmaneo2_b200 import build
+    if build.stale():
+        build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.gpus != world:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run")
+
+    opt = og.CreateOptions(device=local_rank, deviceInit=cfg["device_init"], replayRng=False, shardRank=rank, shardWorld=world)
+    ext = {}
+    if world > 1:
+        cache = {}
+
+        def all_gather(buf, count, stream_ptr):
+            key = (buf, count)
+            if key not in cache:
+                full = torch.as_tensor(_DevArray(buf, count * world), device=f"cuda:{local_rank}")
+                cache[key] = (full, full[rank * count:(rank + 1) * count])
+            full, mine = cache[key]
+            with torch.cuda.stream(ext["s"]):
+                dist.all_gather_into_tensor(full, mine)
+        opt.allGather = all_gather
+    h = og.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=cfg["seed"], options=opt)
+    ext["s"] = torch.cuda.ExternalStream(h.stream(), device=local_rank)
+    h.synchronize()
+
+    # inputs: every prediction/none input gets the chosen stream; generated once, resident in HBM before timing
+    kinds = [args.stream if k in ("noisy", "coherent", "iid") else k for k in cfg["streams"]]
+    has_action = "action" in kinds
+    n_in = len(cfg["inputSizes"])
+    total = W + K
+    host_in = [np.stack([streams.make(k if k != "action" else "iid", t, s) for t in range(total)]) for s, k in zip(cfg["inputSizes"], kinds)]
+    dev_in = [torch.from_numpy(a).to(f"cuda:{local_rank}") for a in host_in]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_device(t0, n):
+        for t in range(t0, t0 + n):
+            h.stepDevice([d[t].data_ptr() for d in dev_in], True)
+
+    run_device(0, W)
+    barrier()
+    for l in range(len(cfg["layerDescs"])):
+        h.takeSCUpdateCount(l)
+    h.profileEnable(True)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.25 if rank == 0 else 0.0)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record(ext["s"])
+    run_device(W, K)
+    e1.record(ext["s"])
+    barrier()
+    wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop(wall0, wall1) if clocks else None
+    prof = h.profileRead()
+    h.profileEnable(False)
+    upd = [h.takeSCUpdateCount(l) for l in range(len(cfg["layerDescs"]))]
+    if dist is not None:
+        t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = K / (ms / 1000.0)
+
+    # ------------------------------------------------------------------------------------------------ e2e (host API)
+    Ke = K
+    barrier()
+    pred_idx = [i for i, t in enumerate(cfg["inputTypes"]) if t != InputType.none]
+    w0 = time.perf_counter()
+    for t in range(W, W + Ke):
+        h.step([a[t] for a in host_in], True)
+        for i in pred_idx:
+            h.getPredictionCs(i)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = sum(int(a[0].nbytes) for a in host_in)
+    d2h = sum(cfg["inputSizes"][i][0] * cfg["inputSizes"][i][1] * 4 for i in pred_idx)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------------------------------------ roofline
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    sites = bytes_per_launch(cfg)
+    counts = tick_counts(cfg, W + K)[W:].sum(axis=0)  # updates per layer inside the timed region
+    alg = {}
+    for (l, kind, b, per_pair) in sites:
+        a = alg.setdefault(kind, 0.0)
+        alg[kind] = a + b * counts[l] / max(world, 1)  # bytes one rank moves (x-slab sharding splits every launch)
+    if "sc_learn" in alg:
+        alg["sc_learn"] += sum(u * 4 * cfg["inputSizes"][0][2] if l == 0 else u * 4 * cfg["layerDescs"][l - 1].hiddenSize[2]
+                               for l, u in enumerate(upd))
+    kernels = {}
+    for kind, (kms, n) in prof.items():
+        if n == 0:
+            continue
+        ab = alg.get(kind, 0.0)
+        kernels[kind] = {"launches": int(n), "ms_per_launch": kms / n, "alg_bytes_per_launch": ab / n if ab else None,
+                         "achieved_gbs": (ab / n) / (kms / n * 1e-3) / 1e9 if ab and kms > 0 else None,
+                         "share_of_step": kms / ms}
+    dom = max((k for k in kernels if kernels[k]["achieved_gbs"]), key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches"])
+    total_alg = sum(alg.values())
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "step_achieved_gbs": total_alg / (ms * 1e-3) / 1e9, "step_frac": total_alg / (ms * 1e-3) / 1e9 / peak,
+                "alg_bytes_per_step_per_gpu": total_alg / K, "kernels": kernels,
+                "sc_pairs_rewritten_per_step": [u / K for u in upd]}
+
+    cpu = None
+    if not args.no_cpu and args.gpus == 1:
+        try:
+            v, info = time_cpu(cfg["sample"], 10, 1, full_cols, budget_s=20.0)
+            info["value"], info["unit"] = v, UNIT
+            cpu = info
+        except Exception as e:  # the baseline must never take the GPU result down with it
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+
+    config.update({"parallelism": f"x-slab sharding over {world} GPU(s)" if world > 1 else "single GPU",
+                   "l2": "per-step weight traffic (GBs) far exceeds the 126 MB L2; no flush needed" if args.workload == "c4"
+                   else "weights exceed L2" if args.workload == "c2" else "L2-resident (latency-bound config)",
+                   "init": "device counter-hash" if cfg["device_init"] else "std::mt19937 in reference order"})
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config, "roofline": roofline, "cpu_baseline": cpu,
+           "e2e": {"value": Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+           "gpu_launches": int(sum(n for _, n in prof.values())), "clocks": clk,
+           "column_steps_per_s": value * sum(ld.hiddenSize[0] * ld.hiddenSize[1] * c for ld, c in zip(cfg["layerDescs"], counts)) / K}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

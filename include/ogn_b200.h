@@ -48,6 +48,13 @@ int ogn_ensemble_size(void *h);
 /* (hidden column, visible column) pairs whose weights SparseCoder l rewrote since the last call: the data-dependent
  * term U of the algorithmic byte count. Synchronises. */
 uint64_t ogn_take_sc_update_count(void *h, int l);
+/* Launch accounting. Kernel kinds, in array order: 0 SparseCoder forward (K2), 1 SparseCoder learn (K3), 2 Predictor
+ * learn+activate (K6+K7+K8), 3 Actor forward (K9), 4 Actor learn (K11). enable(on) resets the counters; with on != 0
+ * every launch is bracketed by CUDA events on the hierarchy's stream. read() synchronises and returns the accumulated
+ * device milliseconds and launch counts per kind (arrays of OGN_KERNEL_KINDS). */
+#define OGN_KERNEL_KINDS 5
+int ogn_profile_enable(void *h, int on);
+int ogn_profile_read(void *h, double *ms, int64_t *launches);
 int ogn_device_count(void);
 
 #ifdef __cplusplus

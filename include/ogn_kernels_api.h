@@ -9,12 +9,16 @@
  * Data layout in HBM:
  *   CSDR            int32 [member][x][y]                      (member = ensemble index, 1 for a single hierarchy)
  *   activations     fp32  [member][x][y][z]
- *   weights, "F"    fp32  [hidden column][slot][visible cell vz][hidden cell hz]   (row gather: hz contiguous)
- *   weights, "R"    fp32  [hidden column][slot][hidden cell hz][visible cell vz]   (SparseCoder reconstruction:
- *                                                                                   vz contiguous); SparseCoder only
- *   slot = (ix - lox)*ny + (iy - loy) inside the clamped receptive field, exactly the reference's CSR order
- *   (Helpers.cpp:236-313); a hidden column's block starts at Vz*Hz*(px[ox]*sy + nx[ox]*py[oy]) in all layouts, so no
- *   index arrays are stored and every offset is 64-bit.
+ *   weights: every gathered "row" (the Z cells selected by one column, one receptive-field slot and one active input
+ *   cell) is contiguous, and P = 32/pow2ceil(Z) (at most 4) y-adjacent columns are PACKED so that the rows a warp
+ *   needs for one visible column form one full 128-byte line:
+ *     "F" (row gather: SparseCoder forward, Predictor, Actor)
+ *         [hidden x][hidden-y pack q][dx][dyU][visible cell vz][p = oy - q*pf][hidden cell hz]
+ *         dyU runs over the UNION of the pack's fields along y (loyf/nyf); slots outside a column's own field are padding
+ *     "R" (SparseCoder reconstruction; SparseCoder only)
+ *         [hidden x][hidden y][dx][visible-y group g = iy/pr][hidden cell hz][iy % pr][visible cell vz]
+ *   With Z = 32 (P = 1) both reduce to the reference's CSR slot order with the cell index moved innermost. Block
+ *   offsets are closed-form products of per-axis prefix sums (no index arrays) and always 64-bit.
  */
 #ifndef OGN_KERNELS_API_H
 #define OGN_KERNELS_API_H
@@ -27,79 +31,131 @@ extern "C" {
 
 #define OGN_MAX_VL 32 /* visible layers per launch (inputs x temporalHorizon of one SparseCoder) */
 
-/* Receptive-field tables of one (hidden grid, visible grid, radius) pairing: initSMLocalRF in closed form
- * (Helpers.cpp:236-313, project() Helpers.h:223-228). The struct and the tables it points to live in device memory. */
+/* Receptive-field geometry of one (hidden grid, visible grid, radius) pairing: initSMLocalRF in closed form
+ * (Helpers.cpp:236-313, project() Helpers.h:223-228). Passed to kernels BY VALUE; the tables it points to live in
+ * device memory. */
 typedef struct ogn_rf {
     int Hx, Hy, Hz;           /* hidden (output) grid */
     int Vx, Vy, Vz;           /* visible (input) grid */
     int radius;
-    int sy;                   /* sum of ny[] over all hidden y */
+    int sy;                   /* sum of ny[] over all hidden y (CSR order) */
+    int pf, pr;               /* pack factors of the F layout (hidden y) and the R layout (visible y) */
+    int syf;                  /* sum of nyf[] over all hidden-y packs */
+    int syr;                  /* sum of ngr[] over all hidden y */
     const int *lox, *nx, *px; /* [Hx] first visible x of the field, extent, exclusive prefix sum of nx */
     const int *loy, *ny, *py; /* [Hy] same along y */
+    const int *loyf, *nyf, *pyf; /* [ceil(Hy/pf)] F packs: first visible y of the union field, extent, prefix sum */
+    const int *ngr, *pyr;     /* [Hy] R: number of visible-y groups (iy/pr) the field touches, prefix sum */
     const int *rlox, *rhix;   /* [Vx] first / last hidden x whose field covers visible x (rlox > rhix: none) */
     const int *rloy, *rhiy;   /* [Vy] */
 } ogn_rf;
 
-/* The weights of one visible layer of one layer object (static after init; an array of these lives in device memory). */
+/* ---- per-launch descriptors, all passed BY VALUE (kernel parameter space): a launch never chases a descriptor
+ * pointer through HBM before it can issue its first weight load. Weight pointers are "virtual bases": the address of
+ * the (possibly not stored) first value of the whole matrix, i.e. storage pointer minus the block offset of the first
+ * stored column, so kernels index with global block offsets. ---- */
+#define OGN_MAX_GEO 4 /* distinct (visible shape, radius) pairings per launch */
+
+typedef struct ogn_fwd_vl {       /* one visible layer of a row-gather launch (SparseCoder forward) */
+    const float *wf;              /* F layout virtual base */
+    const int *cs;                /* visible CSDR [member][Vx][Vy] */
+    int64_t mstride;              /* floats between consecutive ensemble members */
+    int geo;                      /* index into the launch's geometry table */
+    int pad;
+} ogn_fwd_vl;
+
+typedef struct ogn_fwd_args {
+    ogn_rf geo[OGN_MAX_GEO];
+    ogn_fwd_vl vl[OGN_MAX_VL];
+    int nvl;
+} ogn_fwd_args;
+
+typedef struct ogn_learn_vl {     /* one visible layer of a SparseCoder learn launch */
+    float *wf, *wr;               /* F and R layout virtual bases */
+    float *recon;                 /* reconstructions [member][Vx][Vy][Vz] (SparseCoder.h:35) */
+    const int *cs;                /* visible CSDR = reconstruction target */
+    int64_t f_mstride, r_mstride;
+} ogn_learn_vl;
+
+typedef struct ogn_learn_args {   /* visible layers of one launch share the geometry */
+    ogn_rf geo;
+    ogn_learn_vl vl[OGN_MAX_VL];
+    int nvl;
+    int fx0, fx1;                 /* hidden x range whose F copy is stored on this device */
+} ogn_learn_args;
+
+#define OGN_MAX_PRED_VL 8
+typedef struct ogn_pred_vl {
+    float *wf;                    /* F layout virtual base */
+    const int *cs;                /* current inputs (Predictor::activate argument) */
+    const int *cs_prev;           /* VisibleLayer::inputCsPrev (Predictor.h:36) */
+    int *cs_prev_out;             /* where this launch stores cs for the next learn (ping-pong buffer) or NULL */
+    int64_t mstride;
+    int geo, pad;
+} ogn_pred_vl;
+
+typedef struct ogn_pred_args {
+    ogn_rf geo[OGN_MAX_GEO];
+    ogn_pred_vl vl[OGN_MAX_PRED_VL];
+    int nvl;
+} ogn_pred_args;
+
+typedef struct ogn_actor_vl {
+    float *wv, *wa;               /* value (Hz = 1) and action weights, F layout virtual bases */
+    const int *cs;                /* inputs (forward) or the history sample's inputs (learn) */
+    int geo_v, geo_a;             /* geometry indices of the value matrix (Hx,Hy,1) and the action matrix (Hx,Hy,Hz) */
+} ogn_actor_vl;
+
+typedef struct ogn_actor_args {
+    ogn_rf geo[OGN_MAX_GEO];
+    ogn_actor_vl vl[OGN_MAX_PRED_VL];
+    int nvl;
+} ogn_actor_args;
+
+/* Storage description used by the (re)layout / init utilities (host-side struct, not a kernel parameter). */
 typedef struct ogn_wset {
-    const ogn_rf *rf;         /* device pointer */
-    float *wf;                /* F layout, hidden x in [fx0, fx1) */
-    float *wr;                /* R layout, hidden x in [rx0, rx1); NULL unless SparseCoder */
-    float *recon;             /* SparseCoder: reconstructions [member][Vx][Vy][Vz] (SparseCoder.h:35); else NULL */
-    int64_t wf_base, wr_base; /* block offset of column (fx0,0) / (rx0,0): subtracted from global block offsets */
+    float *wf;                /* F layout storage, hidden x in [fx0, fx1) */
+    float *wr;                /* R layout storage, hidden x in [rx0, rx1); NULL unless SparseCoder */
+    int64_t wf_base, wr_base; /* F / R block offset of hidden x = fx0 / rx0 */
     int64_t wf_mstride, wr_mstride; /* floats between consecutive ensemble members */
     int fx0, fx1, rx0, rx1;
-    int vx0, vx1;             /* SparseCoder learn: visible x range this device is responsible for */
 } ogn_wset;
-
-/* Per-launch CSDR pointers, passed by value. */
-typedef struct ogn_cs_args {
-    const int *cs[OGN_MAX_VL];      /* visible CSDR of visible layer v */
-} ogn_cs_args;
-typedef struct ogn_pred_args {
-    const int *cs[8];               /* current inputs (Predictor::activate argument) */
-    const int *cs_prev[8];          /* VisibleLayer::inputCsPrev (Predictor.h:36) */
-    int *cs_prev_out[8];            /* where this launch stores cs for the next learn (ping-pong buffer) or NULL */
-} ogn_pred_args;
 
 const char *ogn_cuda_error_string(int code);
 
 /* K2 — SparseCoder::forward (SparseCoder.cpp:13-43) + multiplyOHVs (SparseMatrix.cpp:260-276) over hidden x in
  * [x0,x1): gather-sum and first-max arg-max. hidden_cs2 (optional) receives a second copy: the next layer's history
  * slot (Hierarchy.cpp:239-246, K5). */
-int ogn_sc_forward(const ogn_wset *wsets, int nvl, const ogn_cs_args *cs_host, int Hx, int Hy, int Hz, int x0, int x1,
-                   int batch, int *hidden_cs, int *hidden_cs2, void *stream);
+int ogn_sc_forward(const ogn_fwd_args *args_host, int Hx, int Hy, int Hz, int x0, int x1, int batch, int *hidden_cs,
+                   int *hidden_cs2, void *stream);
 
 /* K3 — SparseCoder::learn (SparseCoder.cpp:45-83) + multiplyOHVsT/countT/deltaChangedOHVsT (SparseMatrix.cpp:278-294,
- * 215-221, 572-590) for visible layers [v0, v0+nv) which must share (Vx,Vy,Vz). update_count (optional) is incremented
- * by the number of (hidden column, visible column) pairs whose Vz weights were rewritten. */
-int ogn_sc_learn(const ogn_wset *wsets, int v0, int nv, const ogn_cs_args *cs_host, const int *hidden_cs,
-                 const int *hidden_cs_prev, int Hx, int Hy, int Hz, int Vx, int Vy, int Vz, int vx0, int vx1, float alpha,
-                 int batch, unsigned long long *update_count, void *stream);
+ * 215-221, 572-590) for the visible layers in args (same geometry) and visible x in [vx0,vx1). update_count (optional)
+ * is incremented by the number of (hidden column, visible column) pairs whose Vz weights were rewritten. */
+int ogn_sc_learn(const ogn_learn_args *args_host, const int *hidden_cs, const int *hidden_cs_prev, int vx0, int vx1,
+                 float alpha, int batch, unsigned long long *update_count, void *stream);
 
 /* K6+K7+K8 — Predictor::learn (Predictor.cpp:49-70, deltaOHVs SparseMatrix.cpp:488-501), then Predictor::forward
  * (Predictor.cpp:13-47), then inputCs -> inputCsPrev (Predictor.cpp:118-126), over hidden x in [x0,x1).
  * learn != 0 requires target_cs. activations: [member][Hx][Hy][Hz] in/out (read by learn, rewritten by forward). */
-int ogn_pred_step(const ogn_wset *wsets, int nvl, const ogn_pred_args *args_host, int Hx, int Hy, int Hz, int x0, int x1,
-                  int batch, int learn, int activate, const int *target_cs, float alpha, float *activations,
-                  int *hidden_cs, void *stream);
+int ogn_pred_step(const ogn_pred_args *args_host, int Hx, int Hy, int Hz, int x0, int x1, int batch, int learn, int activate,
+                  const int *target_cs, float alpha, float *activations, int *hidden_cs, void *stream);
 
-/* K9 — Actor::forward (Actor.cpp:13-90). value_wsets/action_wsets: nvl entries each. u01[col] is the host-replayed
- * std::generate_canonical<float,24> draw of the column's tile sub-generator. */
-int ogn_actor_forward(const ogn_wset *value_wsets, const ogn_wset *action_wsets, int nvl, const ogn_pred_args *args_host,
-                      int Hx, int Hy, int Hz, const float *u01, float *hidden_values, float *hidden_activations,
-                      int *hidden_cs, void *stream);
+/* K9 — Actor::forward (Actor.cpp:13-90). u01[col] is the host-replayed std::generate_canonical<float,24> draw of the
+ * column's tile sub-generator. */
+int ogn_actor_forward(const ogn_actor_args *args_host, int Hx, int Hy, int Hz, const float *u01, float *hidden_values,
+                      float *hidden_activations, int *hidden_cs, void *stream);
 
-/* K11 — Actor::learn (Actor.cpp:92-185) on one history pair. args.cs = sPrev.inputCs. */
-int ogn_actor_learn(const ogn_wset *value_wsets, const ogn_wset *action_wsets, int nvl, const ogn_pred_args *args_host,
-                    int Hx, int Hy, int Hz, const int *target_cs_prev, const float *hidden_values_prev,
-                    const float *hidden_values, float q, float g, float alpha, float beta, int mimic,
-                    float *hidden_activations, void *stream);
+/* K11 — Actor::learn (Actor.cpp:92-185) on one history pair. args.vl[v].cs = sPrev.inputCs[v]. */
+int ogn_actor_learn(const ogn_actor_args *args_host, int Hx, int Hy, int Hz, const int *target_cs_prev,
+                    const float *hidden_values_prev, const float *hidden_values, float q, float g, float alpha, float beta,
+                    int mimic, float *hidden_activations, void *stream);
 
 /* Weight (re)layout between the reference's CSR value order and the device layouts, for hidden columns
  * [col0, col1) (col = oy + ox*Hy) of one ensemble member. csr is a DEVICE staging buffer holding CSR-order values;
- * csr[0] is the value with global CSR index csr_base (normally the block offset of column col0). which: 0 = F, 1 = R.
- * wset_host / rf_host are HOST copies of the descriptors (their table pointers are device pointers). */
+ * csr[0] is the value with global CSR index csr_base (normally the CSR block offset of column col0). which: 0 = F,
+ * 1 = R. Padding elements of the packed layouts are never written (storage is zero-initialised).
+ * wset_host / rf_host are HOST structs (rf_host's table pointers are device pointers). */
 int ogn_weights_from_csr(const ogn_wset *wset_host, const ogn_rf *rf_host, int member, int which, int col0, int col1,
                          const float *csr, int64_t csr_base, void *stream);
 int ogn_weights_to_csr(const ogn_wset *wset_host, const ogn_rf *rf_host, int member, int which, int col0, int col1,

@@ -44,7 +44,6 @@ void Actor::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, int historyCap
         vw.sets[v].allocate(*ctx, Geometry::get(Int3(hidden.x, hidden.y, 1), vlds[v].size, vlds[v].radius), 1, false, false, 0, hidden.x);
         aw.sets[v].allocate(*ctx, Geometry::get(hidden, vlds[v].size, vlds[v].radius), 1, false, false, 0, hidden.x);
     }
-    vw.commit(*ctx); aw.commit(*ctx);
     acts.allocZero((size_t)ncols * hidden.z, ctx->stream);
     values.allocZero(ncols, ctx->stream);
     hiddenCs.allocZero(ncols, ctx->stream);
@@ -98,11 +97,18 @@ void Actor::stepDevice(ComputeSystem &cs, const int *const *inputDev, const int 
     cudaCheck(cudaMemcpyAsync(m.u01.ptr(), m.u01Host.ptr(), ncols * sizeof(float), cudaMemcpyHostToDevice, ctx.stream), "u01 H2D");
     cudaCheck(cudaEventRecord(m.u01Free, ctx.stream), "cudaEventRecord");
 
-    ogn_pred_args a;
+    ogn_actor_args a;
     std::memset(&a, 0, sizeof(a));
-    for (int v = 0; v < nvl; v++) a.cs[v] = inputDev[v];
-    kernelCheck(ogn_actor_forward(m.vw.devPtr(), m.aw.devPtr(), nvl, &a, Hx, Hy, Hz, m.u01.ptr(), m.values.ptr(), m.acts.ptr(),
-                                  m.hiddenCs.ptr(), ctx.stream), "actor_forward");
+    int ngeo = 0;
+    a.nvl = nvl;
+    for (int v = 0; v < nvl; v++) {
+        a.vl[v].wv = m.vw.sets[v].fBase(); a.vl[v].wa = m.aw.sets[v].fBase(); a.vl[v].cs = inputDev[v];
+        a.vl[v].geo_v = geoIndex(a.geo, ngeo, *m.vw.sets[v].geo);
+        a.vl[v].geo_a = geoIndex(a.geo, ngeo, *m.aw.sets[v].geo);
+    }
+    { LaunchScope ls(ctx, kActorForward);
+    kernelCheck(ogn_actor_forward(&a, Hx, Hy, Hz, m.u01.ptr(), m.values.ptr(), m.acts.ptr(), m.hiddenCs.ptr(), ctx.stream),
+                "actor_forward"); }
     m.csDirty = m.valDirty = true;
 
     // --- push the history sample (K10)
@@ -133,10 +139,11 @@ void Actor::stepDevice(ComputeSystem &cs, const int *const *inputDev, const int 
             }
             consumeKernel2(cs, Hx, Hy);
             for (int v = 0; v < nvl; v++)
-                a.cs[v] = m.histInput[v].ptr() + (size_t)sPrev * visibleLayerDescs[v].size.x * visibleLayerDescs[v].size.y;
-            kernelCheck(ogn_actor_learn(m.vw.devPtr(), m.aw.devPtr(), nvl, &a, Hx, Hy, Hz, m.histTarget.ptr() + (size_t)s * ncols,
+                a.vl[v].cs = m.histInput[v].ptr() + (size_t)sPrev * visibleLayerDescs[v].size.x * visibleLayerDescs[v].size.y;
+            { LaunchScope ls(ctx, kActorLearn);
+            kernelCheck(ogn_actor_learn(&a, Hx, Hy, Hz, m.histTarget.ptr() + (size_t)s * ncols,
                                         m.histValues.ptr() + (size_t)sPrev * ncols, m.values.ptr(), q, g, alpha, beta, mimic ? 1 : 0,
-                                        m.acts.ptr(), ctx.stream), "actor_learn");
+                                        m.acts.ptr(), ctx.stream), "actor_learn"); }
         }
         std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
     }

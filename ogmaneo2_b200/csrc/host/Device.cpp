@@ -2,6 +2,7 @@
 #include "Device.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -26,18 +27,45 @@ DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
     if (prop.major != 10)
         throw std::runtime_error("ogmaneo-b200: device " + std::to_string(device) + " (" + prop.name +
                                  ") is not compute capability 10.x; the kernels are built for sm_100a only");
+    if (const char *g = std::getenv("OGN_L2_FETCH_GRANULARITY")) // experiment knob: 32 / 64 / 128 (a hint to the driver)
+        cudaCheck(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g)), "cudaLimitMaxL2FetchGranularity");
     cudaCheck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
 }
 
 DeviceContext::~DeviceContext() {
+    for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : eventPool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
+}
+
+cudaEvent_t DeviceContext::takeEvent() {
+    if (!eventPool.empty()) { cudaEvent_t e = eventPool.back(); eventPool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaCheck(cudaEventCreate(&e), "cudaEventCreate");
+    return e;
+}
+
+void DeviceContext::profileCollect() {
+    sync();
+    for (auto &r : recs) {
+        float ms = 0.0f;
+        cudaCheck(cudaEventElapsedTime(&ms, r.a, r.b), "cudaEventElapsedTime");
+        kernelMs[r.kind] += ms;
+        eventPool.push_back(r.a); eventPool.push_back(r.b);
+    }
+    recs.clear();
+}
+
+void DeviceContext::profileReset() {
+    profileCollect();
+    for (int k = 0; k < kKernelKinds; k++) { launches[k] = 0; kernelMs[k] = 0.0; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 void Geometry::build(const Int3 &hidden, const Int3 &visible, int r) {
     Hx = hidden.x; Hy = hidden.y; Hz = hidden.z; Vx = visible.x; Vy = visible.y; Vz = visible.z; radius = r;
     // project(): (int)(pos * (float)in / (float)out + 0.5f)   (Helpers.h:223-228, Helpers.cpp:245-246)
-    const float sx = (float)Vx / (float)Hx, syf = (float)Vy / (float)Hy;
+    const float sx = (float)Vx / (float)Hx, syf_ = (float)Vy / (float)Hy;
     auto axis = [r](int H, int V, float scale, std::vector<int> &lo, std::vector<int> &n, std::vector<int> &p, std::vector<int> &rlo,
                     std::vector<int> &rhi) {
         lo.resize(H); n.resize(H); p.resize(H);
@@ -51,23 +79,42 @@ void Geometry::build(const Int3 &hidden, const Int3 &visible, int r) {
         }
         return acc;
     };
-    const int sxTotal = axis(Hx, Vx, sx, lox, nx, px, rlox, rhix);
-    sy = axis(Hy, Vy, syf, loy, ny, py, rloy, rhiy);
+    sxTotal = axis(Hx, Vx, sx, lox, nx, px, rlox, rhix);
+    sy = axis(Hy, Vy, syf_, loy, ny, py, rloy, rhiy);
     nnz = (int64_t)Vz * Hz * (int64_t)sxTotal * sy;
+
+    // packed layouts (include/ogn_kernels_api.h): F packs pf hidden columns along y over the union of their fields,
+    // R groups the visible y of each field by pr
+    pf = packFactor(Hz); pr = packFactor(Vz);
+    const int npk = (Hy + pf - 1) / pf;
+    loyf.assign(npk, 0); nyf.assign(npk, 0); pyf.assign(npk, 0);
+    syf = 0;
+    for (int q = 0; q < npk; q++) {
+        int lo = Vy, hi = -1;
+        for (int o = q * pf; o < std::min(Hy, (q + 1) * pf); o++)
+            if (ny[o] > 0) { lo = std::min(lo, loy[o]); hi = std::max(hi, loy[o] + ny[o] - 1); }
+        loyf[q] = hi >= lo ? lo : 0; nyf[q] = hi >= lo ? hi - lo + 1 : 0; pyf[q] = syf; syf += nyf[q];
+    }
+    ngr.assign(Hy, 0); pyr.assign(Hy, 0);
+    syr = 0;
+    for (int o = 0; o < Hy; o++) {
+        ngr[o] = ny[o] > 0 ? (loy[o] + ny[o] - 1) / pr - loy[o] / pr + 1 : 0;
+        pyr[o] = syr; syr += ngr[o];
+    }
 
     std::vector<int> all;
     auto push = [&all](const std::vector<int> &v) { size_t o = all.size(); all.insert(all.end(), v.begin(), v.end()); return o; };
     const size_t o0 = push(lox), o1 = push(nx), o2 = push(px), o3 = push(loy), o4 = push(ny), o5 = push(py), o6 = push(rlox),
-                 o7 = push(rhix), o8 = push(rloy), o9 = push(rhiy);
+                 o7 = push(rhix), o8 = push(rloy), o9 = push(rhiy), o10 = push(loyf), o11 = push(nyf), o12 = push(pyf),
+                 o13 = push(ngr), o14 = push(pyr);
     tables_.alloc(all.size());
     cudaCheck(cudaMemcpy(tables_.ptr(), all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice), "geometry H2D");
     const int *t = tables_.ptr();
     host.Hx = Hx; host.Hy = Hy; host.Hz = Hz; host.Vx = Vx; host.Vy = Vy; host.Vz = Vz; host.radius = r; host.sy = sy;
+    host.pf = pf; host.pr = pr; host.syf = syf; host.syr = syr;
     host.lox = t + o0; host.nx = t + o1; host.px = t + o2; host.loy = t + o3; host.ny = t + o4; host.py = t + o5;
     host.rlox = t + o6; host.rhix = t + o7; host.rloy = t + o8; host.rhiy = t + o9;
-    devStruct_.alloc(1);
-    cudaCheck(cudaMemcpy(devStruct_.ptr(), &host, sizeof(ogn_rf), cudaMemcpyHostToDevice), "geometry H2D");
-    dev = devStruct_.ptr();
+    host.loyf = t + o10; host.nyf = t + o11; host.pyf = t + o12; host.ngr = t + o13; host.pyr = t + o14;
 }
 
 std::shared_ptr<Geometry> Geometry::get(const Int3 &hidden, const Int3 &visible, int radius) {
@@ -108,19 +155,18 @@ void WeightSet::allocate(DeviceContext &ctx, std::shared_ptr<Geometry> g, int ba
         g->visibleRange(a, b, vx0, vx1);     // visible columns whose reconstruction touches an owned hidden column
         g->hiddenCover(vx0, vx1, rx0, rx1);  // every hidden column those reconstructions sum over (replicas)
     }
-    wf.alloc((size_t)(fCount() * batch));
-    if (hasR) wr.alloc((size_t)(rCount() * batch));
+    wf.allocZero((size_t)(fCount() * batch), ctx.stream); // padding elements of the packed layouts stay zero
+    if (hasR) wr.allocZero((size_t)(rCount() * batch), ctx.stream);
     if (hasRecon) recon.allocZero((size_t)g->Vx * g->Vy * g->Vz * batch, ctx.stream);
 }
 
 ogn_wset WeightSet::desc() const {
     ogn_wset d;
     std::memset(&d, 0, sizeof(d));
-    d.rf = geo->dev;
-    d.wf = wf.ptr(); d.wr = wr.ptr(); d.recon = recon.ptr();
-    d.wf_base = geo->xBlock(fx0); d.wr_base = hasR ? geo->xBlock(rx0) : 0;
+    d.wf = wf.ptr(); d.wr = wr.ptr();
+    d.wf_base = geo->xBlockF(fx0); d.wr_base = hasR ? geo->xBlockR(rx0) : 0;
     d.wf_mstride = fCount(); d.wr_mstride = rCount();
-    d.fx0 = fx0; d.fx1 = fx1; d.rx0 = rx0; d.rx1 = rx1; d.vx0 = vx0; d.vx1 = vx1;
+    d.fx0 = fx0; d.fx1 = fx1; d.rx0 = rx0; d.rx1 = rx1;
     return d;
 }
 
@@ -219,21 +265,18 @@ void WeightSet::cloneFrom(DeviceContext &ctx, const WeightSet &o) {
     wf.cloneFrom(o.wf, ctx.stream); wr.cloneFrom(o.wr, ctx.stream); recon.cloneFrom(o.recon, ctx.stream);
 }
 
-void WeightSetArray::commit(DeviceContext &ctx) {
-    std::vector<ogn_wset> h(sets.size());
-    for (size_t i = 0; i < sets.size(); i++) h[i] = sets[i].desc();
-    dev.alloc(h.size());
-    if (!h.empty()) {
-        cudaCheck(cudaMemcpyAsync(dev.ptr(), h.data(), h.size() * sizeof(ogn_wset), cudaMemcpyHostToDevice, ctx.stream), "wset H2D");
-        ctx.sync(); // h is a stack temporary
-    }
-}
-
 void WeightSetArray::cloneFrom(DeviceContext &ctx, const WeightSetArray &o) {
     sets.clear();
     sets.resize(o.sets.size());
     for (size_t i = 0; i < sets.size(); i++) sets[i].cloneFrom(ctx, o.sets[i]);
-    commit(ctx);
+}
+
+int geoIndex(ogn_rf *table, int &count, const Geometry &g) {
+    for (int i = 0; i < count; i++)
+        if (table[i].lox == g.host.lox) return i; // same device tables <=> same Geometry object
+    if (count >= OGN_MAX_GEO) throw std::runtime_error("ogmaneo-b200: more than 4 distinct visible-layer shapes on one layer");
+    table[count] = g.host;
+    return count++;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

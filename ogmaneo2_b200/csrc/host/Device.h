@@ -22,6 +22,8 @@ namespace detail {
 void cudaCheck(cudaError_t e, const char *what);
 inline void kernelCheck(int code, const char *what) { cudaCheck((cudaError_t)code, what); }
 
+enum KernelKind { kScForward = 0, kScLearn = 1, kPredStep = 2, kActorForward = 3, kActorLearn = 4, kKernelKinds = 5 };
+
 // One device + one stream. Created lazily by ComputeSystem::context(); throws if no sm_100 device is usable.
 struct DeviceContext {
     int device;
@@ -29,6 +31,36 @@ struct DeviceContext {
     explicit DeviceContext(int device);
     ~DeviceContext();
     void sync() const { cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize"); }
+
+    // Launch accounting: counts are always kept; with profiling on, every launch is bracketed by two CUDA events on
+    // `stream` and profileCollect() (after a sync) turns them into per-kind device time.
+    bool profiling = false;
+    long long launches[kKernelKinds] = {0, 0, 0, 0, 0};
+    double kernelMs[kKernelKinds] = {0, 0, 0, 0, 0};
+    struct Rec { cudaEvent_t a, b; int kind; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> eventPool;
+    cudaEvent_t takeEvent();
+    void profileCollect();
+    void profileReset();
+};
+
+// Brackets one kernel launch (see DeviceContext::profiling).
+struct LaunchScope {
+    DeviceContext &c;
+    int kind;
+    cudaEvent_t a = nullptr;
+    LaunchScope(DeviceContext &ctx, int kind_) : c(ctx), kind(kind_) {
+        c.launches[kind]++;
+        if (c.profiling) { a = c.takeEvent(); cudaCheck(cudaEventRecord(a, c.stream), "cudaEventRecord"); }
+    }
+    ~LaunchScope() {
+        if (a) {
+            cudaEvent_t b = c.takeEvent();
+            cudaEventRecord(b, c.stream);
+            c.recs.push_back(DeviceContext::Rec{a, b, kind});
+        }
+    }
 };
 
 template <typename T> class DevBuf {
@@ -99,14 +131,26 @@ private:
 // initSMLocalRF (Helpers.cpp:236-313) in closed form; host tables + their device copies.
 struct Geometry {
     int Hx = 0, Hy = 0, Hz = 0, Vx = 0, Vy = 0, Vz = 0, radius = 0, sy = 0;
+    int pf = 1, pr = 1, syf = 0, syr = 0, sxTotal = 0;
     std::vector<int> lox, nx, px, loy, ny, py, rlox, rhix, rloy, rhiy;
-    int64_t nnz = 0;
-    ogn_rf host{};       // host copy of the descriptor; its table pointers are device pointers
-    const ogn_rf *dev = nullptr;
+    std::vector<int> loyf, nyf, pyf; // per hidden-y pack (F layout)
+    std::vector<int> ngr, pyr;       // per hidden y (R layout)
+    int64_t nnz = 0;                 // weights (CSR order, == the reference's nonZeroValues.size())
+    ogn_rf host{};                   // the by-value kernel descriptor; its table pointers are device pointers
 
     static std::shared_ptr<Geometry> get(const Int3 &hidden, const Int3 &visible, int radius);
+    // pack factor of a layout whose rows hold z cells: must match Pack<G>::P in ogn_kernels.cu
+    static int packFactor(int z) {
+        int g = 1;
+        while (g < z && g < 32) g <<= 1;
+        return g >= 8 ? 32 / g : 4;
+    }
+    // CSR-order block offsets (reference value order)
     int64_t colBlock(int ox, int oy) const { return (int64_t)Vz * Hz * ((int64_t)px[ox] * sy + (int64_t)nx[ox] * py[oy]); }
     int64_t xBlock(int ox) const { return ox >= Hx ? nnz : colBlock(ox, 0); } // offset of column (ox, 0)
+    // device layouts: offset of the first element of hidden x = ox (ox == Hx: total size incl. padding)
+    int64_t xBlockF(int ox) const { return (int64_t)Vz * Hz * pf * (int64_t)(ox >= Hx ? sxTotal : px[ox]) * syf; }
+    int64_t xBlockR(int ox) const { return (int64_t)Vz * Hz * pr * (int64_t)(ox >= Hx ? sxTotal : px[ox]) * syr; }
     int slots(int ox, int oy) const { return nx[ox] * ny[oy]; }
     // visible x range [lo, hi) touched by hidden x in [a, b); hidden x range [lo, hi) covering visible x in [a, b)
     void visibleRange(int a, int b, int &lo, int &hi) const;
@@ -114,7 +158,6 @@ struct Geometry {
 
 private:
     DevBuf<int> tables_;
-    DevBuf<ogn_rf> devStruct_;
     void build(const Int3 &hidden, const Int3 &visible, int radius);
 };
 
@@ -135,8 +178,11 @@ struct WeightSet {
 
     void allocate(DeviceContext &ctx, std::shared_ptr<Geometry> g, int batch, bool hasR, bool hasRecon, int fx0, int fx1);
     ogn_wset desc() const;
-    int64_t fCount() const { return geo->xBlock(fx1) - geo->xBlock(fx0); }
-    int64_t rCount() const { return hasR ? geo->xBlock(rx1) - geo->xBlock(rx0) : 0; }
+    // "virtual bases": storage pointer minus the block offset of the first stored column (see ogn_kernels_api.h)
+    float *fBase() const { return wf.ptr() - geo->xBlockF(fx0); }
+    float *rBase() const { return hasR ? wr.ptr() - geo->xBlockR(rx0) : nullptr; }
+    int64_t fCount() const { return geo->xBlockF(fx1) - geo->xBlockF(fx0); } // floats stored per member (incl. padding)
+    int64_t rCount() const { return hasR ? geo->xBlockR(rx1) - geo->xBlockR(rx0) : 0; }
     // fill(dst, n) must produce the next n values of the matrix in the reference's CSR value order (whole matrix,
     // from index 0 to nnz). Values of columns this device does not store are drawn and dropped.
     void fillFromCSRStream(DeviceContext &ctx, int member, const std::function<void(float *, int64_t)> &fill);
@@ -150,11 +196,11 @@ struct WeightSet {
 
 struct WeightSetArray {
     std::vector<WeightSet> sets;
-    DevBuf<ogn_wset> dev;
-    void commit(DeviceContext &ctx); // (re)upload the descriptor array
-    const ogn_wset *devPtr() const { return dev.ptr(); }
     void cloneFrom(DeviceContext &ctx, const WeightSetArray &o);
 };
+
+// Geometry table of one launch: returns the index of g in `table` (by-value ogn_rf copies), appending if new.
+int geoIndex(ogn_rf *table, int &count, const Geometry &g);
 
 // RNG consumption of the reference's launchers (Helpers.cpp:15-72). seeds != nullptr forces the draws.
 void consumeKernel1(ComputeSystem &cs, int size);

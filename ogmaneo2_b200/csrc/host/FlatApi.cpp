@@ -259,6 +259,23 @@ uint32_t ogn_rng_peek(void *h) {
     std::mt19937 c = ((Handle *)h)->cs.rng;
     return (uint32_t)c();
 }
+int ogn_profile_enable(void *hh, int on) {
+    return guard([&] {
+        detail::DeviceContext &c = ((Handle *)hh)->cs.context();
+        c.profileReset();
+        c.profiling = on != 0;
+    });
+}
+int ogn_profile_read(void *hh, double *ms, int64_t *launches) {
+    return guard([&] {
+        detail::DeviceContext &c = ((Handle *)hh)->cs.context();
+        c.profileCollect();
+        for (int k = 0; k < detail::kKernelKinds; k++) {
+            if (ms) ms[k] = c.kernelMs[k];
+            if (launches) launches[k] = c.launches[k];
+        }
+    });
+}
 int ogn_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

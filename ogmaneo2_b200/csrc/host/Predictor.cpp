@@ -40,7 +40,6 @@ void Predictor::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, const std:
     ws.sets.clear(); ws.sets.resize(vlds.size());
     for (size_t v = 0; v < vlds.size(); v++)
         ws.sets[v].allocate(*ctx, Geometry::get(hidden, vlds[v].size, vlds[v].radius), batch, false, false, x0, x1);
-    ws.commit(*ctx);
     const size_t ncols = (size_t)hidden.x * hidden.y * batch;
     acts.allocZero(ncols * hidden.z, ctx->stream);
     hiddenCs.allocZero(ncols, ctx->stream);
@@ -78,18 +77,23 @@ void Predictor::stepDevice(ComputeSystem &cs, bool learn, const int *targetDev, 
     if (nvl > 8) throw std::runtime_error("ogmaneo-b200: more than 8 visible layers on one Predictor");
     ogn_pred_args a;
     std::memset(&a, 0, sizeof(a));
+    int ngeo = 0;
+    a.nvl = nvl;
     for (int v = 0; v < nvl; v++) {
-        a.cs[v] = activate ? inputDev[v] : nullptr;
-        a.cs_prev[v] = m.prev_[m.prevCur][v].ptr();
-        a.cs_prev_out[v] = activate ? m.prev_[1 - m.prevCur][v].ptr() : nullptr;
+        const WeightSet &w = m.ws.sets[v];
+        a.vl[v].wf = w.fBase(); a.vl[v].mstride = w.fCount(); a.vl[v].geo = geoIndex(a.geo, ngeo, *w.geo);
+        a.vl[v].cs = activate ? inputDev[v] : nullptr;
+        a.vl[v].cs_prev = m.prev_[m.prevCur][v].ptr();
+        a.vl[v].cs_prev_out = activate ? m.prev_[1 - m.prevCur][v].ptr() : nullptr;
     }
     if (learn) consumeKernel2(cs, hiddenSize.x, hiddenSize.y);
     if (activate) {
         consumeKernel2(cs, hiddenSize.x, hiddenSize.y);
         for (int v = 0; v < nvl; v++) consumeKernel1(cs, visibleLayerDescs[v].size.x * visibleLayerDescs[v].size.y);
     }
-    kernelCheck(ogn_pred_step(m.ws.devPtr(), nvl, &a, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, learn ? 1 : 0,
-                              activate ? 1 : 0, targetDev, alpha, m.acts.ptr(), m.hiddenCs.ptr(), ctx.stream), "pred_step");
+    { LaunchScope ls(ctx, kPredStep);
+    kernelCheck(ogn_pred_step(&a, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, learn ? 1 : 0, activate ? 1 : 0,
+                              targetDev, alpha, m.acts.ptr(), m.hiddenCs.ptr(), ctx.stream), "pred_step"); }
     if (learn) std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
     if (activate) {
         m.prevCur = 1 - m.prevCur;

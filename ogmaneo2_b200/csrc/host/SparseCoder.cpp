@@ -36,7 +36,6 @@ void SparseCoder::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, const st
     ws.sets.clear(); ws.sets.resize(vlds.size());
     for (size_t v = 0; v < vlds.size(); v++)
         ws.sets[v].allocate(*ctx, Geometry::get(hidden, vlds[v].size, vlds[v].radius), batch, true, true, x0, x1);
-    ws.commit(*ctx);
     const size_t ncols = (size_t)hidden.x * hidden.y * batch;
     cs_[0].allocZero(ncols, ctx->stream); cs_[1].allocZero(ncols, ctx->stream);
     upd.allocZero(1, ctx->stream);
@@ -68,9 +67,15 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
     DeviceContext &ctx = *m.ctx;
     const int nvl = (int)visibleLayerDescs.size();
     if (nvl > OGN_MAX_VL) throw std::runtime_error("ogmaneo-b200: more than 32 visible layers on one SparseCoder");
-    ogn_cs_args args;
-    std::memset(&args, 0, sizeof(args));
-    for (int v = 0; v < nvl; v++) args.cs[v] = inputCsDev[v];
+    ogn_fwd_args fa;
+    std::memset(&fa, 0, sizeof(fa));
+    int ngeo = 0;
+    fa.nvl = nvl;
+    for (int v = 0; v < nvl; v++) {
+        const WeightSet &w = m.ws.sets[v];
+        fa.vl[v].wf = w.fBase(); fa.vl[v].cs = inputCsDev[v]; fa.vl[v].mstride = w.fCount();
+        fa.vl[v].geo = geoIndex(fa.geo, ngeo, *w.geo);
+    }
 
     const int outIdx = m.prevAliasesCur ? 1 - m.cur : m.cur;
     int *out = m.cs_[outIdx].ptr();
@@ -78,8 +83,9 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
     const bool sharded = m.world > 1;
 
     consumeKernel2(cs, hiddenSize.x, hiddenSize.y);
-    kernelCheck(ogn_sc_forward(m.ws.devPtr(), nvl, &args, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, out,
-                               sharded ? nullptr : copyOut, ctx.stream), "sc_forward");
+    { LaunchScope ls(ctx, kScForward);
+    kernelCheck(ogn_sc_forward(&fa, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, out, sharded ? nullptr : copyOut,
+                               ctx.stream), "sc_forward"); }
     if (sharded) {
         if (!cs.allGather) throw std::runtime_error("ogmaneo-b200: shardWorld > 1 needs ComputeSystem::allGather");
         cs.allGather(cs.allGatherUser, out, (m.x1 - m.x0) * hiddenSize.y, (void *)ctx.stream);
@@ -92,10 +98,19 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
         while (v < nvl) { // one launch per run of visible layers with the same shape and radius
             int e = v + 1;
             while (e < nvl && m.ws.sets[e].geo == m.ws.sets[v].geo) e++;
-            for (int k = v; k < e; k++) consumeKernel2(cs, visibleLayerDescs[k].size.x, visibleLayerDescs[k].size.y);
-            const WeightSet &w = m.ws.sets[v];
-            kernelCheck(ogn_sc_learn(m.ws.devPtr(), v, e - v, &args, out, prev, hiddenSize.x, hiddenSize.y, hiddenSize.z, w.geo->Vx,
-                                     w.geo->Vy, w.geo->Vz, w.vx0, w.vx1, alpha, m.batch, m.upd.ptr(), ctx.stream), "sc_learn");
+            const WeightSet &w0 = m.ws.sets[v];
+            ogn_learn_args la;
+            std::memset(&la, 0, sizeof(la));
+            la.geo = w0.geo->host; la.nvl = e - v; la.fx0 = w0.fx0; la.fx1 = w0.fx1;
+            for (int k = v; k < e; k++) {
+                consumeKernel2(cs, visibleLayerDescs[k].size.x, visibleLayerDescs[k].size.y);
+                const WeightSet &w = m.ws.sets[k];
+                ogn_learn_vl &l = la.vl[k - v];
+                l.wf = w.fBase(); l.wr = w.rBase(); l.recon = w.recon.ptr(); l.cs = inputCsDev[k];
+                l.f_mstride = w.fCount(); l.r_mstride = w.rCount();
+            }
+            { LaunchScope ls(ctx, kScLearn);
+            kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), ctx.stream), "sc_learn"); }
             v = e;
         }
         std::fill(m.wDirty.begin(), m.wDirty.end(), 1);

@@ -21,19 +21,34 @@ namespace {
 
 constexpr int kThreads = 256;
 
-template <int G>
-__device__ __forceinline__ unsigned group_mask() {
-    if (G == 32) return 0xffffffffu;
-    return ((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
+// G = lanes per column (pow2ceil(Z), at most 32); P = columns packed per lane group (the layouts' pack factor);
+// GP = lanes of one pack group. Must match Geometry::packFactor() on the host.
+template <int G> struct Pack {
+    static constexpr int P = G >= 8 ? 32 / G : 4;
+    static constexpr int GP = G * P;
+    static constexpr int B = GP < 16 ? GP : 16; // loads issued per lane before the first dependent add
+};
+
+template <int W>
+__device__ __forceinline__ unsigned lane_mask() { // mask of the W-lane group this thread belongs to
+    if (W == 32) return 0xffffffffu;
+    return ((1u << (W & 31)) - 1u) << ((threadIdx.x & 31) & ~(W - 1));
 }
 
-// Offset of hidden column (ox,oy)'s weight block (identical in the CSR, F and R orders).
-__device__ __forceinline__ long long col_block(const ogn_rf &rf, int ox, int oy) {
+__device__ __forceinline__ long long f_block(const ogn_rf &rf, int ox, int q) { // F block of pack (ox, q)
+    return (long long)rf.Vz * rf.Hz * rf.pf *
+           ((long long)__ldg(rf.px + ox) * rf.syf + (long long)__ldg(rf.nx + ox) * (long long)__ldg(rf.pyf + q));
+}
+__device__ __forceinline__ long long r_block(const ogn_rf &rf, int ox, int oy) { // R block of hidden column (ox, oy)
+    return (long long)rf.Vz * rf.Hz * rf.pr *
+           ((long long)__ldg(rf.px + ox) * rf.syr + (long long)__ldg(rf.nx + ox) * (long long)__ldg(rf.pyr + oy));
+}
+__device__ __forceinline__ long long csr_block(const ogn_rf &rf, int ox, int oy) { // reference CSR order
     return (long long)rf.Vz * rf.Hz *
            ((long long)__ldg(rf.px + ox) * rf.sy + (long long)__ldg(rf.nx + ox) * (long long)__ldg(rf.py + oy));
 }
 
-// (value, index) max over a lane group; the lowest index wins ties. Values must be NaN-free.
+// (value, index) max over a G-lane group; the lowest index wins ties. Values must be NaN-free.
 template <int G>
 __device__ __forceinline__ void group_argmax(unsigned m, float &v, int &i) {
 #pragma unroll
@@ -44,90 +59,142 @@ __device__ __forceinline__ void group_argmax(unsigned m, float &v, int &i) {
     }
 }
 
-// Σ over the receptive field of W_F[col][slot][cs[visible column of slot]][hc] for this lane's hc, in slot order
-// (SparseMatrix::multiplyOHVs, SparseMatrix.cpp:260-276). kReadOnly selects the non-coherent load path.
-template <int G, bool kReadOnly>
-__device__ __forceinline__ float gather_row(unsigned gm, int gl, bool act, const float *w, const int *cs, int lx, int ly,
-                                            int nyv, int nslots, int Vy, int Vz, int Hz) {
-    float p = 0.0f;
-    for (int ch = 0; ch < nslots; ch += G) {
-        const int sm = ch + gl;
-        int cm = 0;
-        if (sm < nslots) cm = __ldg(cs + (lx + sm / nyv) * Vy + ly + sm % nyv);
-        float wv[G];
+template <bool kReadOnly> __device__ __forceinline__ float load_w(const float *a) { return kReadOnly ? __ldg(a) : *a; }
+
+// One pack of P y-adjacent hidden columns seen through one visible layer: the union field the pack group walks and this
+// lane's own column's y-range inside it.
+struct PackCtx {
+    int lx, lyU, nyU, nslotsU; // union field: first visible x / y, y extent, number of union slots
+    int dlo, dn;               // this lane's column covers dyU in [dlo, dlo + dn); dn == 0: lane has no column
+    long long blk;             // F block offset of the pack
+};
+template <int G>
+__device__ __forceinline__ PackCtx pack_ctx(const ogn_rf &rf, int ox, int q, int p) {
+    PackCtx c;
+    c.lx = __ldg(rf.lox + ox);
+    c.lyU = __ldg(rf.loyf + q);
+    c.nyU = __ldg(rf.nyf + q);
+    c.nslotsU = __ldg(rf.nx + ox) * c.nyU;
+    const int oy = q * rf.pf + p;
+    c.dlo = 0; c.dn = 0;
+    if (p < rf.pf && oy < rf.Hy) { c.dlo = __ldg(rf.loy + oy) - c.lyU; c.dn = __ldg(rf.ny + oy); }
+    c.blk = f_block(rf, ox, q);
+    return c;
+}
+
+// Σ over this lane's column's receptive field of W_F[...][cs[visible column]][p][hc], in the reference's slot order
+// (SparseMatrix::multiplyOHVs, SparseMatrix.cpp:260-276). w = pack block + p*Hz + hc (hc clamped into range).
+// The GP lanes of the pack group walk the UNION field together: each lane turns "its" union slot of the current GP slots
+// into a line offset (one CSDR read), offsets are broadcast by shuffle and the lines are loaded UNCONDITIONALLY (slot
+// index clamped, padding elements are real memory), so a batch of loads is in flight before the first add. Only the
+// adds are guarded (slot inside this column's own field), which keeps every column's sum order exact.
+// bit j: union slot (chunk start + j) lies inside this lane's own column's field. With P == 1 the union IS the field.
+template <int G>
+__device__ __forceinline__ unsigned slot_mask(unsigned gm, int dym, const PackCtx &c) {
+    constexpr int GP = Pack<G>::GP;
+    if (Pack<G>::P == 1) return 0xffffffffu;
+    unsigned m = 0;
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            const int cj = __shfl_sync(gm, cm, j, G);
-            wv[j] = 0.0f;
-            if (act && ch + j < nslots) {
-                const float *a = w + ((long long)(ch + j) * Vz + cj) * Hz;
-                wv[j] = kReadOnly ? __ldg(a) : *a;
+    for (int j = 0; j < GP; ++j)
+        m |= ((unsigned)(__shfl_sync(gm, dym, j, GP) - c.dlo) < (unsigned)c.dn ? 1u : 0u) << j;
+    return m;
+}
+
+template <int G, bool kReadOnly>
+__device__ __forceinline__ float gather_pack(unsigned gm, int gl, const float *w, const int *cs, const PackCtx &c, int Vy, int Vz,
+                                             int rowW) {
+    constexpr int GP = Pack<G>::GP, B = Pack<G>::B;
+    float p = 0.0f;
+    for (int ch = 0; ch < c.nslotsU; ch += GP) {
+        const int sm = min(ch + gl, c.nslotsU - 1);
+        const int dxm = sm / c.nyU, dym = sm - dxm * c.nyU;
+        const int cm = __ldg(cs + (c.lx + dxm) * Vy + c.lyU + dym);
+        const int om = (sm * Vz + cm) * rowW;
+        const int left = c.nslotsU - ch; // valid slots in this chunk (may exceed GP)
+        const unsigned vm = slot_mask<G>(gm, dym, c) & (left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
+#pragma unroll
+        for (int sub = 0; sub < GP; sub += B) {
+            if (sub < left) {
+                float wv[B];
+#pragma unroll
+                for (int j = 0; j < B; ++j) wv[j] = load_w<kReadOnly>(w + __shfl_sync(gm, om, sub + j, GP));
+#pragma unroll
+                for (int j = 0; j < B; ++j)
+                    if ((vm >> (sub + j)) & 1u) p += wv[j];
             }
         }
-#pragma unroll
-        for (int j = 0; j < G; ++j)
-            if (ch + j < nslots) p += wv[j];
     }
     return p;
 }
 
-// W_F[col][slot][cs[...]][hc] += delta over the receptive field (SparseMatrix::deltaOHVs, SparseMatrix.cpp:488-501).
+// W_F[...][cs[...]][p][hc] += delta over this lane's column's field (SparseMatrix::deltaOHVs, SparseMatrix.cpp:488-501).
 template <int G>
-__device__ __forceinline__ void delta_row(unsigned gm, int gl, bool act, float *w, const int *cs, float delta, int lx, int ly,
-                                          int nyv, int nslots, int Vy, int Vz, int Hz) {
-    for (int ch = 0; ch < nslots; ch += G) {
-        const int sm = ch + gl;
-        int cm = 0;
-        if (sm < nslots) cm = __ldg(cs + (lx + sm / nyv) * Vy + ly + sm % nyv);
-        float wv[G];
+__device__ __forceinline__ void delta_pack(unsigned gm, int gl, bool act, float *w, const int *cs, float delta, const PackCtx &c, int Vy,
+                                           int Vz, int rowW) {
+    constexpr int GP = Pack<G>::GP, B = Pack<G>::B;
+    for (int ch = 0; ch < c.nslotsU; ch += GP) {
+        const int sm = min(ch + gl, c.nslotsU - 1);
+        const int dxm = sm / c.nyU, dym = sm - dxm * c.nyU;
+        const int cm = __ldg(cs + (c.lx + dxm) * Vy + c.lyU + dym);
+        const int om = (sm * Vz + cm) * rowW;
+        const int left = c.nslotsU - ch;
+        unsigned vm = slot_mask<G>(gm, dym, c) & (left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
+        if (!act) vm = 0;
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            const int cj = __shfl_sync(gm, cm, j, G);
-            wv[j] = 0.0f;
-            if (act && ch + j < nslots) wv[j] = w[((long long)(ch + j) * Vz + cj) * Hz];
-        }
+        for (int sub = 0; sub < GP; sub += B) {
+            if (sub < left) {
+                float wv[B];
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            const int cj = __shfl_sync(gm, cm, j, G);
-            if (act && ch + j < nslots) w[((long long)(ch + j) * Vz + cj) * Hz] = wv[j] + delta;
+                for (int j = 0; j < B; ++j) wv[j] = w[__shfl_sync(gm, om, sub + j, GP)];
+#pragma unroll
+                for (int j = 0; j < B; ++j) {
+                    const int o = __shfl_sync(gm, om, sub + j, GP);
+                    if ((vm >> (sub + j)) & 1u) w[o] = wv[j] + delta;
+                }
+            }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2: SparseCoder::forward (SparseCoder.cpp:13-43)
+// K2: SparseCoder::forward (SparseCoder.cpp:13-43). One pack group per hidden-y pack.
 template <int G>
 __global__ void __launch_bounds__(kThreads)
-k_sc_forward(const ogn_wset *__restrict__ wsets, int nvl, ogn_cs_args cs, int Hx, int Hy, int Hz, int x0, int ncols,
+k_sc_forward(const __grid_constant__ ogn_fwd_args A, int Hx, int Hy, int Hz, int x0, int npacks, int packsPerRow,
              int *__restrict__ out0, int *__restrict__ out1) {
-    const int gl = threadIdx.x & (G - 1);
-    const int group = (blockIdx.x * kThreads + threadIdx.x) / G;
-    if (group >= ncols) return; // whole groups leave together
-    const unsigned gm = group_mask<G>();
+    constexpr int P = Pack<G>::P, GP = Pack<G>::GP;
+    const int gl = threadIdx.x & (GP - 1);
+    const int pack = (blockIdx.x * kThreads + threadIdx.x) / GP;
+    if (pack >= npacks) return; // whole pack groups leave together
+    const unsigned gm = lane_mask<GP>(), sm = lane_mask<G>();
     const int member = blockIdx.y;
-    const int ox = x0 + group / Hy, oy = group % Hy;
+    const int ox = x0 + pack / packsPerRow, q = pack % packsPerRow;
+    const int p = gl / G, hl = gl % G;
+    const int oy = q * P + p;
+    const bool colValid = oy < Hy;
 
     int bestIdx = 0;
     float bestVal = -999999.0f;
     for (int hc0 = 0; hc0 < Hz; hc0 += G) {
-        const int hc = hc0 + gl;
-        const bool act = hc < Hz;
+        const int hc = hc0 + hl;
+        const bool act = hc < Hz && colValid;
+        const int hcl = hc < Hz ? hc : Hz - 1;
         float sum = 0.0f;
-        for (int v = 0; v < nvl; ++v) {
-            const ogn_wset ws = wsets[v];
-            const ogn_rf rf = *ws.rf;
-            const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
-            const float *w = ws.wf + (col_block(rf, ox, oy) - ws.wf_base + (long long)member * ws.wf_mstride) + hc;
-            const int *c = cs.cs[v] + (long long)member * rf.Vx * rf.Vy;
-            sum += gather_row<G, true>(gm, gl, act, w, c, lx, ly, nyv, nxv * nyv, rf.Vy, rf.Vz, rf.Hz);
+        for (int v = 0; v < A.nvl; ++v) {
+            const ogn_fwd_vl &vl = A.vl[v];
+            const ogn_rf &rf = A.geo[vl.geo];
+            const PackCtx c = pack_ctx<G>(rf, ox, q, p);
+            const float *w = vl.wf + (c.blk + (long long)member * vl.mstride) + p * Hz + hcl;
+            const int *cs = vl.cs + (long long)member * rf.Vx * rf.Vy;
+            sum += gather_pack<G, true>(gm, gl, w, cs, c, rf.Vy, rf.Vz, P * Hz);
         }
         // sequential rule: `if (sum > max)` from (idx 0, -999999); NaN never wins
         float v = (act && sum > -999999.0f) ? sum : (act ? -999999.0f : -INFINITY);
         int i = act ? hc : 0x7fffffff;
-        group_argmax<G>(gm, v, i);
+        group_argmax<G>(sm, v, i);
         if (v > bestVal) { bestVal = v; bestIdx = i; }
     }
-    if (gl == 0) {
+    if (hl == 0 && colValid) {
         const long long o = (long long)member * Hx * Hy + ox * Hy + oy;
         out0[o] = bestIdx;
         if (out1) out1[o] = bestIdx;
@@ -135,73 +202,101 @@ k_sc_forward(const ogn_wset *__restrict__ wsets, int nvl, ogn_cs_args cs, int Hx
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K3: SparseCoder::learn (SparseCoder.cpp:45-83). One lane group per visible column, lane = visible cell vc.
-struct CoverItem { long long offR; long long offF; int flags; }; // flags: bit0 changed, bit1 F copy stored here
+// K3: SparseCoder::learn (SparseCoder.cpp:45-83). One pack group per group of pr y-adjacent visible columns;
+// lane = (visible column of the pack, visible cell vc).
+struct CoverItem { long long offR; int mask; }; // line offset in R, bit pv set: hidden column covers visible column pv
 
 template <int G>
-__device__ __forceinline__ CoverItem cover_item(const ogn_wset &ws, const ogn_rf &rf, int k, int ncov, int ncy, int hx0, int hy0,
-                                                int vx, int vy, const int *hcs, const int *hcsPrev) {
+__device__ __forceinline__ CoverItem cover_item(const ogn_rf &rf, int k, int ncyU, int hx0, int hy0U, int vx, int vyBase,
+                                                const int *hcs) {
+    constexpr int P = Pack<G>::P;
     CoverItem it;
-    it.offR = 0; it.offF = 0; it.flags = 0;
-    if (k < ncov) {
-        const int ox = hx0 + k / ncy, oy = hy0 + k % ncy;
-        const int h = ox * rf.Hy + oy;
-        const int hc = __ldg(hcs + h);
-        const int s = (vx - __ldg(rf.lox + ox)) * __ldg(rf.ny + oy) + (vy - __ldg(rf.loy + oy));
-        const long long blk = col_block(rf, ox, oy);
-        it.offR = blk - ws.wr_base + ((long long)s * rf.Hz + hc) * rf.Vz;
-        it.offF = blk - ws.wf_base + (long long)s * rf.Vz * rf.Hz + hc;
-        it.flags = (hc != __ldg(hcsPrev + h) ? 1 : 0) | ((ox >= ws.fx0 && ox < ws.fx1) ? 2 : 0);
-    }
+    const int ox = hx0 + k / ncyU, oy = hy0U + k % ncyU;
+    const int hc = __ldg(hcs + ox * rf.Hy + oy);
+    const int ylo = __ldg(rf.loy + oy), yn = __ldg(rf.ny + oy);
+    const int dx = vx - __ldg(rf.lox + ox);
+    const int gi = vyBase / P - ylo / P; // visible-y group index inside this hidden column's field
+    it.offR = r_block(rf, ox, oy) + (((long long)dx * __ldg(rf.ngr + oy) + gi) * rf.Hz + hc) * (P * rf.Vz);
+    it.mask = 0;
+#pragma unroll
+    for (int pv = 0; pv < P; ++pv)
+        if ((unsigned)(vyBase + pv - ylo) < (unsigned)yn && vyBase + pv < rf.Vy) it.mask |= 1 << pv;
     return it;
 }
 
 template <int G>
 __global__ void __launch_bounds__(kThreads)
-k_sc_learn(const ogn_wset *__restrict__ wsets, int v0, ogn_cs_args cs, const int *__restrict__ hcsAll,
-           const int *__restrict__ hcsPrevAll, int vx0, int ncols, float alpha, unsigned long long *updCount) {
-    const int gl = threadIdx.x & (G - 1);
-    const int group = (blockIdx.x * kThreads + threadIdx.x) / G;
-    if (group >= ncols) return;
-    const unsigned gm = group_mask<G>();
+k_sc_learn(const __grid_constant__ ogn_learn_args A, const int *__restrict__ hcsAll, const int *__restrict__ hcsPrevAll, int vx0,
+           int npacks, int packsPerRow, float alpha, unsigned long long *updCount) {
+    constexpr int P = Pack<G>::P, GP = Pack<G>::GP, B = Pack<G>::B;
+    const int gl = threadIdx.x & (GP - 1);
+    const int pack = (blockIdx.x * kThreads + threadIdx.x) / GP;
+    if (pack >= npacks) return;
+    const unsigned gm = lane_mask<GP>(), sm = lane_mask<G>();
     const int member = blockIdx.y;
-    const int v = v0 + blockIdx.z;
-    const ogn_wset ws = wsets[v];
-    const ogn_rf rf = *ws.rf;
+    const ogn_learn_vl &vl = A.vl[blockIdx.z];
+    const ogn_rf &rf = A.geo;
     const int Vz = rf.Vz;
-    const int vx = vx0 + group / rf.Vy, vy = group % rf.Vy;
-    const long long vcol = (long long)member * rf.Vx * rf.Vy + vx * rf.Vy + vy;
-    const int target = __ldg(cs.cs[v] + vcol);
+    const int vx = vx0 + pack / packsPerRow, vyBase = (pack % packsPerRow) * P;
+    const int pv = gl / G, vl_ = gl % G;
+    const int vy = vyBase + pv;
+    const bool colValid = vy < rf.Vy;
+    const int vyc = colValid ? vy : rf.Vy - 1;
+    const long long vcol = (long long)member * rf.Vx * rf.Vy + vx * rf.Vy + vyc;
+    const int target = __ldg(vl.cs + vcol);
     const int *hcs = hcsAll + (long long)member * rf.Hx * rf.Hy;
     const int *hcsPrev = hcsPrevAll + (long long)member * rf.Hx * rf.Hy;
-    float *wr = ws.wr + (long long)member * ws.wr_mstride;
-    float *wf = ws.wf + (long long)member * ws.wf_mstride;
-    float *recon = ws.recon + vcol * Vz;
+    float *wr = vl.wr + (long long)member * vl.r_mstride;
+    float *wf = vl.wf + (long long)member * vl.f_mstride;
+    float *recon = vl.recon + vcol * Vz;
 
-    const int hx0 = __ldg(rf.rlox + vx), hx1 = __ldg(rf.rhix + vx), hy0 = __ldg(rf.rloy + vy), hy1 = __ldg(rf.rhiy + vy);
+    // cover sets: own (for the count and the update) and the pack's union along y (walked together)
+    const int hx0 = __ldg(rf.rlox + vx), hx1 = __ldg(rf.rhix + vx);
+    const int hy0 = __ldg(rf.rloy + vyc), hy1 = __ldg(rf.rhiy + vyc);
     const int ncx = max(0, hx1 - hx0 + 1), ncy = max(0, hy1 - hy0 + 1);
     const int ncov = ncx * ncy; // == countT(visibleIndex) / hiddenSize.z
+    int hy0U = rf.Hy, hy1U = -1;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        const int y = vyBase + k;
+        if (y < rf.Vy) {
+            const int a = __ldg(rf.rloy + y), b = __ldg(rf.rhiy + y);
+            if (b >= a) { hy0U = min(hy0U, a); hy1U = max(hy1U, b); }
+        }
+    }
+    const int ncyU = max(0, hy1U - hy0U + 1), ncovU = ncx * ncyU;
 
     // reconstruction + arg-max with the reference's `sum > max || maxIndex == -1` rule
     int bestIdx = -1;
     float bestVal = -999999.0f;
-    float myRecon = 0.0f; // recon of vc = gl when Vz <= G
+    float myRecon = 0.0f; // recon of vc = lane's cell when Vz <= G
     for (int vc0 = 0; vc0 < Vz; vc0 += G) {
-        const int vc = vc0 + gl;
-        const bool act = vc < Vz;
+        const int vc = vc0 + vl_;
+        const bool act = vc < Vz && colValid;
+        const int vcl = vc < Vz ? vc : Vz - 1;
         float sum = 0.0f;
-        for (int ch = 0; ch < ncov; ch += G) {
-            const CoverItem mine = cover_item<G>(ws, rf, ch + gl, ncov, ncy, hx0, hy0, vx, vy, hcs, hcsPrev);
-            float wv[G];
+        for (int ch = 0; ch < ncovU; ch += GP) {
+            const CoverItem mine = cover_item<G>(rf, min(ch + gl, ncovU - 1), ncyU, hx0, hy0U, vx, vyBase, hcs);
+            const int left = ncovU - ch;
+            // bit j: hidden column (chunk start + j) covers this lane's visible column
+            unsigned vm = 0xffffffffu;
+            if (P != 1) {
+                vm = 0;
 #pragma unroll
-            for (int j = 0; j < G; ++j) {
-                const long long off = __shfl_sync(gm, mine.offR, j, G);
-                wv[j] = 0.0f;
-                if (act && ch + j < ncov) wv[j] = wr[off + vc];
+                for (int j = 0; j < GP; ++j) vm |= (unsigned)((__shfl_sync(gm, mine.mask, j, GP) >> pv) & 1) << j;
             }
+            vm &= left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
 #pragma unroll
-            for (int j = 0; j < G; ++j)
-                if (ch + j < ncov) sum += wv[j];
+            for (int sub = 0; sub < GP; sub += B) {
+                if (sub < left) {
+                    float wv[B];
+#pragma unroll
+                    for (int j = 0; j < B; ++j) wv[j] = wr[__shfl_sync(gm, mine.offR, sub + j, GP) + pv * Vz + vcl];
+#pragma unroll
+                    for (int j = 0; j < B; ++j)
+                        if ((vm >> (sub + j)) & 1u) sum += wv[j];
+                }
+            }
         }
         sum = sum / (float)ncov;
         if (act) recon[vc] = sum;
@@ -212,79 +307,99 @@ k_sc_learn(const ogn_wset *__restrict__ wsets, int v0, ogn_cs_args cs, const int
         else if (vc == 0) val = (sum != sum) ? INFINITY : sum;
         else val = (sum != sum) ? -INFINITY : sum;
         int idx = act ? vc : 0x7fffffff;
-        group_argmax<G>(gm, val, idx);
+        group_argmax<G>(sm, val, idx);
         if (bestIdx == -1 || val > bestVal) { bestVal = val; bestIdx = idx; }
     }
-    if (bestIdx == target) return;
+    if (!colValid || bestIdx == target) return; // from here on the G lanes of one visible column work on their own
 
     // delta rule on the weights of hidden columns whose state changed (deltaChangedOHVsT, SparseMatrix.cpp:572-590)
     int nupd = 0;
     for (int vc0 = 0; vc0 < Vz; vc0 += G) {
-        const int vc = vc0 + gl;
+        const int vc = vc0 + vl_;
         const bool act = vc < Vz;
         float r = myRecon;
         if (vc0 != 0 && act) r = recon[vc];
         const float delta = alpha * ((vc == target ? 1.0f : 0.0f) - ogn_expf(r));
         for (int ch = 0; ch < ncov; ch += G) {
-            const CoverItem mine = cover_item<G>(ws, rf, ch + gl, ncov, ncy, hx0, hy0, vx, vy, hcs, hcsPrev);
+            // lane's item: one hidden column of this visible column's own cover set
+            long long offR = 0, offF = 0;
+            int fl = 0;
+            if (ch + vl_ < ncov) {
+                const int k = ch + vl_;
+                const int ox = hx0 + k / ncy, oy = hy0 + k % ncy;
+                const int h = ox * rf.Hy + oy;
+                const int hc = __ldg(hcs + h);
+                const int ylo = __ldg(rf.loy + oy);
+                const int dx = vx - __ldg(rf.lox + ox);
+                offR = r_block(rf, ox, oy) +
+                       ((((long long)dx * __ldg(rf.ngr + oy) + (vy / P - ylo / P)) * rf.Hz + hc) * P + (vy % P)) * Vz;
+                const int qh = oy / rf.pf, ph = oy % rf.pf;
+                offF = f_block(rf, ox, qh) +
+                       (((long long)dx * __ldg(rf.nyf + qh) + (vy - __ldg(rf.loyf + qh))) * Vz * rf.pf + ph) * rf.Hz + hc;
+                fl = (hc != __ldg(hcsPrev + h) ? 1 : 0) | ((ox >= A.fx0 && ox < A.fx1) ? 2 : 0);
+            }
 #pragma unroll 4
             for (int j = 0; j < G; ++j) {
-                const long long offR = __shfl_sync(gm, mine.offR, j, G);
-                const long long offF = __shfl_sync(gm, mine.offF, j, G);
-                const int fl = __shfl_sync(gm, mine.flags, j, G);
-                if (ch + j < ncov && (fl & 1)) {
+                const long long oR = __shfl_sync(sm, offR, j, G);
+                const long long oF = __shfl_sync(sm, offF, j, G);
+                const int f = __shfl_sync(sm, fl, j, G);
+                if (f & 1) {
                     if (act) {
-                        const float nw = wr[offR + vc] + delta;
-                        wr[offR + vc] = nw;
-                        if (fl & 2) wf[offF + (long long)vc * rf.Hz] = nw;
+                        const float nw = wr[oR + vc] + delta;
+                        wr[oR + vc] = nw;
+                        if (f & 2) wf[oF + (long long)vc * rf.pf * rf.Hz] = nw;
                     }
                     if (vc0 == 0) nupd++;
                 }
             }
         }
     }
-    if (updCount && gl == 0 && nupd) atomicAdd(updCount, (unsigned long long)nupd);
+    if (updCount && vl_ == 0 && nupd) atomicAdd(updCount, (unsigned long long)nupd);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // K6+K7+K8: Predictor::learn (Predictor.cpp:49-70), Predictor::forward (:13-47), inputCs -> inputCsPrev (:118-126)
 template <int G>
 __global__ void __launch_bounds__(kThreads)
-k_pred_step(const ogn_wset *__restrict__ wsets, int nvl, ogn_pred_args a, int Hx, int Hy, int Hz, int x0, int ncols, int learn,
-            int activate, const int *__restrict__ target, float alpha, float *acts, int *__restrict__ hiddenCs) {
+k_pred_step(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int Hz, int x0, int npacks, int packsPerRow, int learn, int activate,
+            const int *__restrict__ target, float alpha, float *acts, int *__restrict__ hiddenCs) {
+    constexpr int P = Pack<G>::P, GP = Pack<G>::GP;
     const int member = blockIdx.y;
     // K8: every thread of the grid helps copying the inputs into the *other* inputCsPrev buffer (never read here)
     if (activate) {
         const int tid = blockIdx.x * kThreads + threadIdx.x, nth = gridDim.x * kThreads;
-        for (int v = 0; v < nvl; ++v) {
-            if (!a.cs_prev_out[v]) continue;
-            const ogn_rf *rfp = wsets[v].rf;
-            const int n = rfp->Vx * rfp->Vy;
+        for (int v = 0; v < A.nvl; ++v) {
+            if (!A.vl[v].cs_prev_out) continue;
+            const int n = A.geo[A.vl[v].geo].Vx * A.geo[A.vl[v].geo].Vy;
             const long long mo = (long long)member * n;
-            for (int i = tid; i < n; i += nth) a.cs_prev_out[v][mo + i] = __ldg(a.cs[v] + mo + i);
+            for (int i = tid; i < n; i += nth) A.vl[v].cs_prev_out[mo + i] = __ldg(A.vl[v].cs + mo + i);
         }
     }
-    const int gl = threadIdx.x & (G - 1);
-    const int group = (blockIdx.x * kThreads + threadIdx.x) / G;
-    if (group >= ncols) return;
-    const unsigned gm = group_mask<G>();
-    const int ox = x0 + group / Hy, oy = group % Hy;
-    const long long col = (long long)member * Hx * Hy + ox * Hy + oy;
+    const int gl = threadIdx.x & (GP - 1);
+    const int pack = (blockIdx.x * kThreads + threadIdx.x) / GP;
+    if (pack >= npacks) return;
+    const unsigned gm = lane_mask<GP>(), sm = lane_mask<G>();
+    const int ox = x0 + pack / packsPerRow, q = pack % packsPerRow;
+    const int p = gl / G, hl = gl % G;
+    const int oy = q * P + p;
+    const bool colValid = oy < Hy;
+    const long long col = (long long)member * Hx * Hy + ox * Hy + (colValid ? oy : Hy - 1);
 
     if (learn) {
         const int t = __ldg(target + col);
         for (int hc0 = 0; hc0 < Hz; hc0 += G) {
-            const int hc = hc0 + gl;
-            const bool act = hc < Hz;
+            const int hc = hc0 + hl;
+            const bool act = hc < Hz && colValid;
+            const int hcl = hc < Hz ? hc : Hz - 1;
             float delta = 0.0f;
             if (act) delta = alpha * ((hc == t ? 1.0f : -1.0f) - ogn_tanhf(acts[col * Hz + hc]));
-            for (int v = 0; v < nvl; ++v) {
-                const ogn_wset ws = wsets[v];
-                const ogn_rf rf = *ws.rf;
-                const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
-                float *w = ws.wf + (col_block(rf, ox, oy) - ws.wf_base + (long long)member * ws.wf_mstride) + hc;
-                const int *c = a.cs_prev[v] + (long long)member * rf.Vx * rf.Vy;
-                delta_row<G>(gm, gl, act, w, c, delta, lx, ly, nyv, nxv * nyv, rf.Vy, rf.Vz, rf.Hz);
+            for (int v = 0; v < A.nvl; ++v) {
+                const ogn_pred_vl &vl = A.vl[v];
+                const ogn_rf &rf = A.geo[vl.geo];
+                const PackCtx c = pack_ctx<G>(rf, ox, q, p);
+                float *w = vl.wf + (c.blk + (long long)member * vl.mstride) + p * Hz + hcl;
+                const int *cs = vl.cs_prev + (long long)member * rf.Vx * rf.Vy;
+                delta_pack<G>(gm, gl, act, w, cs, delta, c, rf.Vy, rf.Vz, P * Hz);
             }
         }
     }
@@ -293,78 +408,105 @@ k_pred_step(const ogn_wset *__restrict__ wsets, int nvl, ogn_pred_args a, int Hx
     int bestIdx = 0;
     float bestVal = -999999.0f;
     for (int hc0 = 0; hc0 < Hz; hc0 += G) {
-        const int hc = hc0 + gl;
-        const bool act = hc < Hz;
+        const int hc = hc0 + hl;
+        const bool act = hc < Hz && colValid;
+        const int hcl = hc < Hz ? hc : Hz - 1;
         float sum = 0.0f;
         int count = 0;
-        for (int v = 0; v < nvl; ++v) {
-            const ogn_wset ws = wsets[v];
-            const ogn_rf rf = *ws.rf;
-            const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
-            const float *w = ws.wf + (col_block(rf, ox, oy) - ws.wf_base + (long long)member * ws.wf_mstride) + hc;
-            const int *c = a.cs[v] + (long long)member * rf.Vx * rf.Vy;
-            sum += gather_row<G, false>(gm, gl, act, w, c, lx, ly, nyv, nxv * nyv, rf.Vy, rf.Vz, rf.Hz);
-            count += nxv * nyv;
+        for (int v = 0; v < A.nvl; ++v) {
+            const ogn_pred_vl &vl = A.vl[v];
+            const ogn_rf &rf = A.geo[vl.geo];
+            const PackCtx c = pack_ctx<G>(rf, ox, q, p);
+            const float *w = vl.wf + (c.blk + (long long)member * vl.mstride) + p * Hz + hcl;
+            const int *cs = vl.cs + (long long)member * rf.Vx * rf.Vy;
+            sum += gather_pack<G, false>(gm, gl, w, cs, c, rf.Vy, rf.Vz, P * Hz);
+            count += c.dn * (c.nslotsU / max(c.nyU, 1)); // own field: nx * ny
         }
         sum = sum / (float)count;
         if (act) acts[col * Hz + hc] = sum;
         float v = (act && sum > -999999.0f) ? sum : (act ? -999999.0f : -INFINITY);
         int i = act ? hc : 0x7fffffff;
-        group_argmax<G>(gm, v, i);
+        group_argmax<G>(sm, v, i);
         if (v > bestVal) { bestVal = v; bestIdx = i; }
     }
-    if (gl == 0) hiddenCs[col] = bestIdx;
+    if (hl == 0 && colValid) hiddenCs[col] = bestIdx;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Actor helpers: value row = the single row of the (Hx,Hy,1) value matrix; all lanes of the group compute it redundantly
-// (same addresses -> broadcast loads).
-template <int G>
-__device__ __forceinline__ float actor_value_sum(unsigned gm, int gl, const ogn_wset *vw, int nvl, const int *const *cs, int ox,
-                                                 int oy, int *countOut) {
-    float value = 0.0f;
-    int count = 0;
-    for (int v = 0; v < nvl; ++v) {
-        const ogn_wset ws = vw[v];
-        const ogn_rf rf = *ws.rf;
-        const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
-        const float *w = ws.wf + (col_block(rf, ox, oy) - ws.wf_base);
-        value += gather_row<G, false>(gm, gl, true, w, cs[v], lx, ly, nyv, nxv * nyv, rf.Vy, rf.Vz, 1);
-        count += nxv * nyv;
-    }
-    *countOut = count;
-    return value;
+// Actor. One pack group per hidden-y pack of action columns (template G from the action Z). The value matrix has
+// Hz = 1, i.e. its own geometry with pack factor 4: lane 0 of every column gathers the value row with the generic
+// single-lane routines below (action layers are tiny; SURVEY.md: "negligible bytes, correctness-critical RNG").
+__device__ __forceinline__ float value_row_sum(const ogn_rf &rf, const float *wv, const int *cs, int ox, int oy, int *countOut) {
+    const int q = oy / rf.pf, p = oy % rf.pf;
+    const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
+    const int lyU = __ldg(rf.loyf + q), nyU = __ldg(rf.nyf + q);
+    const float *w = wv + f_block(rf, ox, q) + p;
+    float sum = 0.0f;
+    for (int dx = 0; dx < nxv; ++dx)
+        for (int dy = 0; dy < nyv; ++dy) {
+            const int c = __ldg(cs + (lx + dx) * rf.Vy + ly + dy);
+            sum += w[((long long)(dx * nyU + (ly + dy - lyU)) * rf.Vz + c) * rf.pf];
+        }
+    *countOut = nxv * nyv;
+    return sum;
+}
+__device__ __forceinline__ void value_row_delta(const ogn_rf &rf, float *wv, const int *cs, int ox, int oy, float delta) {
+    const int q = oy / rf.pf, p = oy % rf.pf;
+    const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
+    const int lyU = __ldg(rf.loyf + q), nyU = __ldg(rf.nyf + q);
+    float *w = wv + f_block(rf, ox, q) + p;
+    for (int dx = 0; dx < nxv; ++dx)
+        for (int dy = 0; dy < nyv; ++dy) {
+            const int c = __ldg(cs + (lx + dx) * rf.Vy + ly + dy);
+            w[((long long)(dx * nyU + (ly + dy - lyU)) * rf.Vz + c) * rf.pf] += delta;
+        }
 }
 
-// action activations of this lane's hc: (Σ_v gather) / count, stored raw; returns them through acts[]
+// value (lane 0 of the column, broadcast) and the total slot count
 template <int G>
-__device__ __forceinline__ void actor_action_acts(unsigned gm, int gl, const ogn_wset *aw, int nvl, const int *const *cs, int ox,
-                                                  int oy, int Hz, int count, float *acts /* column base */) {
+__device__ __forceinline__ float actor_value(unsigned sm, int hl, bool colValid, const ogn_actor_args &A, int ox, int oy, int *countOut) {
+    float value = 0.0f;
+    int count = 0;
+    if (hl == 0 && colValid)
+        for (int v = 0; v < A.nvl; ++v) {
+            int n;
+            value += value_row_sum(A.geo[A.vl[v].geo_v], A.vl[v].wv, A.vl[v].cs, ox, oy, &n);
+            count += n;
+        }
+    *countOut = __shfl_sync(sm, count, 0, G);
+    return __shfl_sync(sm, value, 0, G);
+}
+
+// raw action activations (Σ_v gather) / count into acts[] (column base)
+template <int G>
+__device__ __forceinline__ void actor_action_acts(unsigned gm, unsigned sm, int gl, int p, int hl, bool colValid, const ogn_actor_args &A,
+                                                  int ox, int q, int Hz, int count, float *acts) {
+    constexpr int P = Pack<G>::P;
     for (int hc0 = 0; hc0 < Hz; hc0 += G) {
-        const int hc = hc0 + gl;
-        const bool act = hc < Hz;
+        const int hc = hc0 + hl;
+        const bool act = hc < Hz && colValid;
+        const int hcl = hc < Hz ? hc : Hz - 1;
         float sum = 0.0f;
-        for (int v = 0; v < nvl; ++v) {
-            const ogn_wset ws = aw[v];
-            const ogn_rf rf = *ws.rf;
-            const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
-            const float *w = ws.wf + (col_block(rf, ox, oy) - ws.wf_base) + hc;
-            sum += gather_row<G, false>(gm, gl, act, w, cs[v], lx, ly, nyv, nxv * nyv, rf.Vy, rf.Vz, rf.Hz);
+        for (int v = 0; v < A.nvl; ++v) {
+            const ogn_rf &rf = A.geo[A.vl[v].geo_a];
+            const PackCtx c = pack_ctx<G>(rf, ox, q, p);
+            const float *w = A.vl[v].wa + c.blk + p * Hz + hcl;
+            sum += gather_pack<G, false>(gm, gl, w, A.vl[v].cs, c, rf.Vy, rf.Vz, P * Hz);
         }
         sum = sum / (float)count;
         if (act) acts[hc] = sum;
     }
-    __syncwarp(gm);
+    __syncwarp(sm);
 }
 
 // softmax numerators in place (Actor.cpp:57-69 / :159-171): acts[hc] = expf(acts[hc] - max); returns Σ in ascending hc order.
 template <int G>
-__device__ __forceinline__ float actor_softmax(unsigned gm, int gl, int Hz, float *acts) {
+__device__ __forceinline__ float actor_softmax(unsigned sm, int hl, int Hz, float *acts) {
     float m = -999999.0f;
     for (int hc = 0; hc < Hz; ++hc) m = fmaxf(m, __ldcg(acts + hc)); // every lane scans the same Hz values (L2 reads)
-    __syncwarp(gm);
-    for (int hc = gl; hc < Hz; hc += G) acts[hc] = ogn_expf(__ldcg(acts + hc) - m);
-    __syncwarp(gm);
+    __syncwarp(sm);
+    for (int hc = hl; hc < Hz; hc += G) acts[hc] = ogn_expf(__ldcg(acts + hc) - m);
+    __syncwarp(sm);
     float total = 0.0f;
     for (int hc = 0; hc < Hz; ++hc) total += __ldcg(acts + hc);
     return total;
@@ -373,104 +515,136 @@ __device__ __forceinline__ float actor_softmax(unsigned gm, int gl, int Hz, floa
 // K9: Actor::forward (Actor.cpp:13-90)
 template <int G>
 __global__ void __launch_bounds__(kThreads)
-k_actor_forward(const ogn_wset *__restrict__ vw, const ogn_wset *__restrict__ aw, int nvl, ogn_pred_args a, int Hx, int Hy, int Hz,
+k_actor_forward(const __grid_constant__ ogn_actor_args A, int Hx, int Hy, int Hz, int npacks, int packsPerRow,
                 const float *__restrict__ u01, float *hiddenValues, float *hiddenActs, int *hiddenCs) {
-    const int gl = threadIdx.x & (G - 1);
-    const int group = (blockIdx.x * kThreads + threadIdx.x) / G;
-    if (group >= Hx * Hy) return;
-    const unsigned gm = group_mask<G>();
-    const int ox = group / Hy, oy = group % Hy;
+    constexpr int P = Pack<G>::P, GP = Pack<G>::GP;
+    const int gl = threadIdx.x & (GP - 1);
+    const int pack = (blockIdx.x * kThreads + threadIdx.x) / GP;
+    if (pack >= npacks) return;
+    const unsigned gm = lane_mask<GP>(), sm = lane_mask<G>();
+    const int ox = pack / packsPerRow, q = pack % packsPerRow;
+    const int p = gl / G, hl = gl % G;
+    const int oy = q * P + p;
+    const bool colValid = oy < Hy;
+    const int col = ox * Hy + (colValid ? oy : Hy - 1);
     int count;
-    const float value = actor_value_sum<G>(gm, gl, vw, nvl, a.cs, ox, oy, &count);
-    if (gl == 0) hiddenValues[group] = value / (float)count;
-    float *acts = hiddenActs + (long long)group * Hz;
-    actor_action_acts<G>(gm, gl, aw, nvl, a.cs, ox, oy, Hz, count, acts);
-    const float total = actor_softmax<G>(gm, gl, Hz, acts);
-    if (gl == 0) {
+    const float value = actor_value<G>(sm, hl, colValid, A, ox, oy, &count);
+    if (hl == 0 && colValid) hiddenValues[col] = value / (float)count;
+    float *acts = hiddenActs + (long long)col * Hz;
+    actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, ox, q, Hz, count, acts);
+    if (!colValid) return;
+    const float total = actor_softmax<G>(sm, hl, Hz, acts);
+    if (hl == 0) {
         // std::uniform_real_distribution<float>(0, total): canonical * (b - a) + a   (libstdc++ bits/random.h)
-        const float cusp = u01[group] * (total - 0.0f) + 0.0f;
+        const float cusp = u01[col] * (total - 0.0f) + 0.0f;
         int select = 0;
         float sumSoFar = 0.0f;
         for (int hc = 0; hc < Hz; ++hc) {
             sumSoFar += __ldcg(acts + hc);
             if (sumSoFar >= cusp) { select = hc; break; }
         }
-        hiddenCs[group] = select;
+        hiddenCs[col] = select;
     }
 }
 
 // K11: Actor::learn (Actor.cpp:92-185)
 template <int G>
 __global__ void __launch_bounds__(kThreads)
-k_actor_learn(const ogn_wset *__restrict__ vw, const ogn_wset *__restrict__ aw, int nvl, ogn_pred_args a, int Hx, int Hy, int Hz,
-              const int *__restrict__ targetPrev, const float *__restrict__ valuesPrev, const float *__restrict__ hiddenValues,
-              float q, float g, float alpha, float beta, int mimic, float *hiddenActs) {
-    const int gl = threadIdx.x & (G - 1);
-    const int group = (blockIdx.x * kThreads + threadIdx.x) / G;
-    if (group >= Hx * Hy) return;
-    const unsigned gm = group_mask<G>();
-    const int ox = group / Hy, oy = group % Hy;
+k_actor_learn(const __grid_constant__ ogn_actor_args A, int Hx, int Hy, int Hz, int npacks, int packsPerRow,
+              const int *__restrict__ targetPrev, const float *__restrict__ valuesPrev, const float *__restrict__ hiddenValues, float q_,
+              float g, float alpha, float beta, int mimic, float *hiddenActs) {
+    constexpr int P = Pack<G>::P, GP = Pack<G>::GP;
+    const int gl = threadIdx.x & (GP - 1);
+    const int pack = (blockIdx.x * kThreads + threadIdx.x) / GP;
+    if (pack >= npacks) return;
+    const unsigned gm = lane_mask<GP>(), sm = lane_mask<G>();
+    const int ox = pack / packsPerRow, q = pack % packsPerRow;
+    const int p = gl / G, hl = gl % G;
+    const int oy = q * P + p;
+    const bool colValid = oy < Hy;
+    const int col = ox * Hy + (colValid ? oy : Hy - 1);
 
-    const float newValue = q + g * hiddenValues[group];
+    const float newValue = q_ + g * hiddenValues[col];
     int count;
-    float value = actor_value_sum<G>(gm, gl, vw, nvl, a.cs, ox, oy, &count);
+    float value = actor_value<G>(sm, hl, colValid, A, ox, oy, &count);
     value = value / (float)count;
     const float tdErrorValue = newValue - value;
     const float deltaValue = alpha * tdErrorValue;
-    for (int v = 0; v < nvl; ++v) { // value row += deltaValue: slots spread over the lanes (distinct addresses)
-        const ogn_wset ws = vw[v];
-        const ogn_rf rf = *ws.rf;
-        const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
-        float *w = ws.wf + (col_block(rf, ox, oy) - ws.wf_base);
-        for (int s = gl; s < nxv * nyv; s += G) {
-            const int c = __ldg(a.cs[v] + (lx + s / nyv) * rf.Vy + ly + s % nyv);
-            w[(long long)s * rf.Vz + c] += deltaValue;
-        }
-    }
-    const float tdErrorAction = newValue - valuesPrev[group];
-    const int target = targetPrev[group];
-    float *acts = hiddenActs + (long long)group * Hz;
-    actor_action_acts<G>(gm, gl, aw, nvl, a.cs, ox, oy, Hz, count, acts);
-    const float total = actor_softmax<G>(gm, gl, Hz, acts);
+    if (hl == 0 && colValid)
+        for (int v = 0; v < A.nvl; ++v) value_row_delta(A.geo[A.vl[v].geo_v], A.vl[v].wv, A.vl[v].cs, ox, oy, deltaValue);
+    const float tdErrorAction = newValue - valuesPrev[col];
+    const int target = targetPrev[col];
+    float *acts = hiddenActs + (long long)col * Hz;
+    actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, ox, q, Hz, count, acts);
+    float total = 1.0f;
+    if (colValid) total = actor_softmax<G>(sm, hl, Hz, acts);
     for (int hc0 = 0; hc0 < Hz; hc0 += G) {
-        const int hc = hc0 + gl;
-        const bool act = hc < Hz;
+        const int hc = hc0 + hl;
+        const bool act = hc < Hz && colValid;
+        const int hcl = hc < Hz ? hc : Hz - 1;
         float delta = 0.0f;
         if (act)
             delta = (mimic ? beta : (tdErrorAction > 0.0f ? beta : -beta)) *
                     ((hc == target ? 1.0f : 0.0f) - __ldcg(acts + hc) / fmaxf(0.0001f, total));
-        for (int v = 0; v < nvl; ++v) {
-            const ogn_wset ws = aw[v];
-            const ogn_rf rf = *ws.rf;
-            const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
-            float *w = ws.wf + (col_block(rf, ox, oy) - ws.wf_base) + hc;
-            delta_row<G>(gm, gl, act, w, a.cs[v], delta, lx, ly, nyv, nxv * nyv, rf.Vy, rf.Vz, rf.Hz);
+        for (int v = 0; v < A.nvl; ++v) {
+            const ogn_rf &rf = A.geo[A.vl[v].geo_a];
+            const PackCtx c = pack_ctx<G>(rf, ox, q, p);
+            float *w = A.vl[v].wa + c.blk + p * Hz + hcl;
+            delta_pack<G>(gm, gl, act, w, A.vl[v].cs, delta, c, rf.Vy, rf.Vz, P * Hz);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Weight (re)layout. One block per hidden column; element e of the column block is addressed in the *device* order.
-// which: 0 = F [slot][vz][hz], 1 = R [slot][hz][vz]; CSR order is [hz][slot][vz].
-__device__ __forceinline__ long long csr_index_of(int which, long long e, int nslots, int Vz, int Hz) {
-    int s, vz, hz;
-    if (which == 0) { hz = (int)(e % Hz); vz = (int)((e / Hz) % Vz); s = (int)(e / ((long long)Hz * Vz)); }
-    else { vz = (int)(e % Vz); hz = (int)((e / Vz) % Hz); s = (int)(e / ((long long)Hz * Vz)); }
-    return ((long long)hz * nslots + s) * Vz + vz;
+// Weight (re)layout, init and checks. One block per hidden column; threads walk the column's CSR-order elements
+// e = (hz * nslots + s) * Vz + vz and compute the element's position in the packed device layouts.
+struct ColMap {
+    int nslots, nyv, ly, Vz, Hz;
+    long long csr;        // CSR block offset
+    long long fBase;      // F: pack block offset + p*Hz;        element = fBase + ((dx*nyU + dy + fdy)*Vz + vz)*pf*Hz + hz
+    int nyU, fdy, fRow;
+    long long rBase;      // R: column block offset;             element = rBase + (((dx*ngr + (ly+dy)/pr - ly/pr)*Hz + hz)*pr + (ly+dy)%pr)*Vz + vz
+    int ngr, pr;
+};
+__device__ __forceinline__ ColMap col_map(const ogn_rf &rf, int ox, int oy) {
+    ColMap m;
+    m.nyv = rf.ny[oy]; m.nslots = rf.nx[ox] * m.nyv; m.ly = rf.loy[oy]; m.Vz = rf.Vz; m.Hz = rf.Hz;
+    m.csr = csr_block(rf, ox, oy);
+    const int q = oy / rf.pf, p = oy % rf.pf;
+    m.fBase = f_block(rf, ox, q) + (long long)p * rf.Hz;
+    m.nyU = rf.nyf[q]; m.fdy = m.ly - rf.loyf[q]; m.fRow = rf.pf * rf.Hz;
+    m.rBase = r_block(rf, ox, oy);
+    m.ngr = rf.ngr[oy]; m.pr = rf.pr;
+    return m;
+}
+__device__ __forceinline__ void split_csr(const ColMap &m, long long e, int &hz, int &dx, int &dy, int &vz) {
+    vz = (int)(e % m.Vz);
+    const long long t = e / m.Vz;
+    const int s = (int)(t % m.nslots);
+    hz = (int)(t / m.nslots);
+    dx = s / m.nyv; dy = s % m.nyv;
+}
+__device__ __forceinline__ long long f_index(const ColMap &m, int hz, int dx, int dy, int vz) {
+    return m.fBase + ((long long)(dx * m.nyU + dy + m.fdy) * m.Vz + vz) * m.fRow + hz;
+}
+__device__ __forceinline__ long long r_index(const ColMap &m, int hz, int dx, int dy, int vz) {
+    const int iy = m.ly + dy;
+    return m.rBase + ((((long long)dx * m.ngr + (iy / m.pr - m.ly / m.pr)) * m.Hz + hz) * m.pr + iy % m.pr) * m.Vz + vz;
 }
 
-__global__ void k_layout(ogn_rf rf, float *dev, long long devBase, int which, int col0, float *csr, long long csrBase, int toCsr) {
+// which: 0 = F, 1 = R
+__global__ void k_layout(const __grid_constant__ ogn_rf rf, float *dev, long long devBase, int which, int col0, float *csr,
+                         long long csrBase, int toCsr) {
     const int col = col0 + blockIdx.x;
-    const int ox = col / rf.Hy, oy = col % rf.Hy;
-    const int nslots = rf.nx[ox] * rf.ny[oy];
-    const long long blk = col_block(rf, ox, oy);
-    const long long n = (long long)nslots * rf.Vz * rf.Hz;
-    float *d = dev + (blk - devBase);
-    float *c = csr + (blk - csrBase);
+    const ColMap m = col_map(rf, col / rf.Hy, col % rf.Hy);
+    const long long n = (long long)m.nslots * m.Vz * m.Hz;
+    float *c = csr + (m.csr - csrBase);
     for (long long e = threadIdx.x; e < n; e += blockDim.x) {
-        const long long ci = csr_index_of(which, e, nslots, rf.Vz, rf.Hz);
-        if (toCsr) c[ci] = d[e];
-        else d[e] = c[ci];
+        int hz, dx, dy, vz;
+        split_csr(m, e, hz, dx, dy, vz);
+        const long long di = (which == 0 ? f_index(m, hz, dx, dy, vz) : r_index(m, hz, dx, dy, vz)) - devBase;
+        if (toCsr) c[e] = dev[di];
+        else dev[di] = c[e];
     }
 }
 
@@ -480,36 +654,34 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
-__global__ void k_init_hash(ogn_rf rf, float *wf, long long wfBase, int fx0, int fx1, float *wr, long long wrBase, int rx0, int rx1,
-                            int col0, uint64_t key, float lo, float hi) {
+__global__ void k_init_hash(const __grid_constant__ ogn_rf rf, float *wf, long long wfBase, int fx0, int fx1, float *wr, long long wrBase,
+                            int rx0, int rx1, int col0, uint64_t key, float lo, float hi) {
     const int col = col0 + blockIdx.x;
-    const int ox = col / rf.Hy, oy = col % rf.Hy;
-    const int nslots = rf.nx[ox] * rf.ny[oy];
-    const long long blk = col_block(rf, ox, oy);
-    const long long n = (long long)nslots * rf.Vz * rf.Hz;
+    const int ox = col / rf.Hy;
+    const ColMap m = col_map(rf, ox, col % rf.Hy);
+    const long long n = (long long)m.nslots * m.Vz * m.Hz;
     const bool inF = wf && ox >= fx0 && ox < fx1, inR = wr && ox >= rx0 && ox < rx1;
     const float span = hi - lo;
-    for (long long e = threadIdx.x; e < n; e += blockDim.x) { // e in F order so the F stores coalesce
-        const int hz = (int)(e % rf.Hz), vz = (int)((e / rf.Hz) % rf.Vz), s = (int)(e / ((long long)rf.Hz * rf.Vz));
-        const long long ci = blk + ((long long)hz * nslots + s) * rf.Vz + vz; // global CSR index of this weight
-        const uint32_t u24 = (uint32_t)(mix64(key + (uint64_t)ci * 0xD1B54A32D192ED03ull) >> 40);
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+        int hz, dx, dy, vz;
+        split_csr(m, e, hz, dx, dy, vz);
+        const uint32_t u24 = (uint32_t)(mix64(key + (uint64_t)(m.csr + e) * 0xD1B54A32D192ED03ull) >> 40);
         const float val = (float)u24 * (1.0f / 16777216.0f) * span + lo;
-        if (inF) wf[blk - wfBase + e] = val;
-        if (inR) wr[blk - wrBase + ((long long)s * rf.Hz + hz) * rf.Vz + vz] = val;
+        if (inF) wf[f_index(m, hz, dx, dy, vz) - wfBase] = val;
+        if (inR) wr[r_index(m, hz, dx, dy, vz) - wrBase] = val;
     }
 }
 
-__global__ void k_fr_mismatch(ogn_rf rf, const float *wf, long long wfBase, const float *wr, long long wrBase, int col0,
-                              unsigned long long *count) {
+__global__ void k_fr_mismatch(const __grid_constant__ ogn_rf rf, const float *wf, long long wfBase, const float *wr, long long wrBase,
+                              int col0, unsigned long long *count) {
     const int col = col0 + blockIdx.x;
-    const int ox = col / rf.Hy, oy = col % rf.Hy;
-    const int nslots = rf.nx[ox] * rf.ny[oy];
-    const long long blk = col_block(rf, ox, oy);
-    const long long n = (long long)nslots * rf.Vz * rf.Hz;
+    const ColMap m = col_map(rf, col / rf.Hy, col % rf.Hy);
+    const long long n = (long long)m.nslots * m.Vz * m.Hz;
     unsigned long long bad = 0;
     for (long long e = threadIdx.x; e < n; e += blockDim.x) {
-        const int hz = (int)(e % rf.Hz), vz = (int)((e / rf.Hz) % rf.Vz), s = (int)(e / ((long long)rf.Hz * rf.Vz));
-        const float a = wf[blk - wfBase + e], b = wr[blk - wrBase + ((long long)s * rf.Hz + hz) * rf.Vz + vz];
+        int hz, dx, dy, vz;
+        split_csr(m, e, hz, dx, dy, vz);
+        const float a = wf[f_index(m, hz, dx, dy, vz) - wfBase], b = wr[r_index(m, hz, dx, dy, vz) - wrBase];
         if (__float_as_uint(a) != __float_as_uint(b)) bad++;
     }
     if (bad) atomicAdd(count, bad);
@@ -547,64 +719,65 @@ extern "C" {
 
 const char *ogn_cuda_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
-int ogn_sc_forward(const ogn_wset *wsets, int nvl, const ogn_cs_args *cs, int Hx, int Hy, int Hz, int x0, int x1, int batch,
-                   int *hidden_cs, int *hidden_cs2, void *stream) {
-    if (nvl > OGN_MAX_VL) return (int)cudaErrorInvalidValue;
-    const int ncols = (x1 - x0) * Hy;
-    if (ncols <= 0 || batch <= 0) return 0;
-    const int g = group_lanes(Hz);
-    dim3 grid((unsigned)(((long long)ncols * g + kThreads - 1) / kThreads), (unsigned)batch);
-    OGN_DISPATCH_G(g, (k_sc_forward<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(wsets, nvl, *cs, Hx, Hy, Hz, x0, ncols,
-                                                                                 hidden_cs, hidden_cs2)));
+static inline int pack_factor(int g) { return g >= 8 ? 32 / g : 4; }
+
+int ogn_sc_forward(const ogn_fwd_args *args, int Hx, int Hy, int Hz, int x0, int x1, int batch, int *hidden_cs, int *hidden_cs2,
+                   void *stream) {
+    if (args->nvl > OGN_MAX_VL) return (int)cudaErrorInvalidValue;
+    if (x1 <= x0 || batch <= 0 || Hy <= 0) return 0;
+    const int g = group_lanes(Hz), P = pack_factor(g), ppr = (Hy + P - 1) / P, npacks = (x1 - x0) * ppr;
+    for (int v = 0; v < args->nvl; v++)
+        if (args->geo[args->vl[v].geo].pf != P) return (int)cudaErrorInvalidValue;
+    dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);
+    OGN_DISPATCH_G(g, (k_sc_forward<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, x0, npacks, ppr, hidden_cs,
+                                                                                 hidden_cs2)));
     return launch_status();
 }
 
-int ogn_sc_learn(const ogn_wset *wsets, int v0, int nv, const ogn_cs_args *cs, const int *hidden_cs, const int *hidden_cs_prev,
-                 int Hx, int Hy, int Hz, int Vx, int Vy, int Vz, int vx0, int vx1, float alpha, int batch,
+int ogn_sc_learn(const ogn_learn_args *args, const int *hidden_cs, const int *hidden_cs_prev, int vx0, int vx1, float alpha, int batch,
                  unsigned long long *update_count, void *stream) {
-    (void)Hx; (void)Hy; (void)Hz; (void)Vx;
-    const int ncols = (vx1 - vx0) * Vy;
-    if (ncols <= 0 || batch <= 0 || nv <= 0) return 0;
-    const int g = group_lanes(Vz);
-    dim3 grid((unsigned)(((long long)ncols * g + kThreads - 1) / kThreads), (unsigned)batch, (unsigned)nv);
-    OGN_DISPATCH_G(g, (k_sc_learn<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(wsets, v0, *cs, hidden_cs, hidden_cs_prev, vx0,
-                                                                               ncols, alpha, update_count)));
+    if (vx1 <= vx0 || batch <= 0 || args->nvl <= 0) return 0;
+    if (args->nvl > OGN_MAX_VL) return (int)cudaErrorInvalidValue;
+    const int g = group_lanes(args->geo.Vz), P = pack_factor(g), ppr = (args->geo.Vy + P - 1) / P, npacks = (vx1 - vx0) * ppr;
+    if (args->geo.pr != P) return (int)cudaErrorInvalidValue;
+    dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch, (unsigned)args->nvl);
+    OGN_DISPATCH_G(g, (k_sc_learn<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, hidden_cs, hidden_cs_prev, vx0, npacks, ppr, alpha,
+                                                                               update_count)));
     return launch_status();
 }
 
-int ogn_pred_step(const ogn_wset *wsets, int nvl, const ogn_pred_args *args, int Hx, int Hy, int Hz, int x0, int x1, int batch,
-                  int learn, int activate, const int *target_cs, float alpha, float *activations, int *hidden_cs, void *stream) {
-    if (nvl > 8) return (int)cudaErrorInvalidValue;
-    const int ncols = (x1 - x0) * Hy;
-    if (ncols <= 0 || batch <= 0) return 0;
-    const int g = group_lanes(Hz);
-    dim3 grid((unsigned)(((long long)ncols * g + kThreads - 1) / kThreads), (unsigned)batch);
-    OGN_DISPATCH_G(g, (k_pred_step<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(wsets, nvl, *args, Hx, Hy, Hz, x0, ncols, learn,
-                                                                                activate, target_cs, alpha, activations,
-                                                                                hidden_cs)));
+int ogn_pred_step(const ogn_pred_args *args, int Hx, int Hy, int Hz, int x0, int x1, int batch, int learn, int activate,
+                  const int *target_cs, float alpha, float *activations, int *hidden_cs, void *stream) {
+    if (args->nvl > OGN_MAX_PRED_VL) return (int)cudaErrorInvalidValue;
+    if (x1 <= x0 || batch <= 0 || Hy <= 0) return 0;
+    const int g = group_lanes(Hz), P = pack_factor(g), ppr = (Hy + P - 1) / P, npacks = (x1 - x0) * ppr;
+    for (int v = 0; v < args->nvl; v++)
+        if (args->geo[args->vl[v].geo].pf != P) return (int)cudaErrorInvalidValue;
+    dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);
+    OGN_DISPATCH_G(g, (k_pred_step<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, x0, npacks, ppr, learn, activate,
+                                                                                target_cs, alpha, activations, hidden_cs)));
     return launch_status();
 }
 
-int ogn_actor_forward(const ogn_wset *vw, const ogn_wset *aw, int nvl, const ogn_pred_args *args, int Hx, int Hy, int Hz,
-                      const float *u01, float *hidden_values, float *hidden_activations, int *hidden_cs, void *stream) {
-    if (nvl > 8) return (int)cudaErrorInvalidValue;
-    const int g = group_lanes(Hz);
-    dim3 grid((unsigned)(((long long)Hx * Hy * g + kThreads - 1) / kThreads));
-    OGN_DISPATCH_G(g, (k_actor_forward<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(vw, aw, nvl, *args, Hx, Hy, Hz, u01,
-                                                                                    hidden_values, hidden_activations,
-                                                                                    hidden_cs)));
+int ogn_actor_forward(const ogn_actor_args *args, int Hx, int Hy, int Hz, const float *u01, float *hidden_values,
+                      float *hidden_activations, int *hidden_cs, void *stream) {
+    if (args->nvl > OGN_MAX_PRED_VL) return (int)cudaErrorInvalidValue;
+    const int g = group_lanes(Hz), P = pack_factor(g), ppr = (Hy + P - 1) / P, npacks = Hx * ppr;
+    dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads));
+    OGN_DISPATCH_G(g, (k_actor_forward<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, npacks, ppr, u01, hidden_values,
+                                                                                    hidden_activations, hidden_cs)));
     return launch_status();
 }
 
-int ogn_actor_learn(const ogn_wset *vw, const ogn_wset *aw, int nvl, const ogn_pred_args *args, int Hx, int Hy, int Hz,
-                    const int *target_cs_prev, const float *hidden_values_prev, const float *hidden_values, float q, float g_,
-                    float alpha, float beta, int mimic, float *hidden_activations, void *stream) {
-    if (nvl > 8) return (int)cudaErrorInvalidValue;
-    const int g = group_lanes(Hz);
-    dim3 grid((unsigned)(((long long)Hx * Hy * g + kThreads - 1) / kThreads));
-    OGN_DISPATCH_G(g, (k_actor_learn<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(vw, aw, nvl, *args, Hx, Hy, Hz, target_cs_prev,
-                                                                                  hidden_values_prev, hidden_values, q, g_,
-                                                                                  alpha, beta, mimic, hidden_activations)));
+int ogn_actor_learn(const ogn_actor_args *args, int Hx, int Hy, int Hz, const int *target_cs_prev, const float *hidden_values_prev,
+                    const float *hidden_values, float q, float g_, float alpha, float beta, int mimic, float *hidden_activations,
+                    void *stream) {
+    if (args->nvl > OGN_MAX_PRED_VL) return (int)cudaErrorInvalidValue;
+    const int g = group_lanes(Hz), P = pack_factor(g), ppr = (Hy + P - 1) / P, npacks = Hx * ppr;
+    dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads));
+    OGN_DISPATCH_G(g, (k_actor_learn<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, npacks, ppr, target_cs_prev,
+                                                                                  hidden_values_prev, hidden_values, q, g_, alpha, beta,
+                                                                                  mimic, hidden_activations)));
     return launch_status();
 }
 

@@ -45,6 +45,8 @@ _PRODUCT_SIGS = {
     "ensemble_size": (C.c_int, [_VP]),
     "take_sc_update_count": (C.c_uint64, [_VP, C.c_int]),
     "device_count": (C.c_int, []),
+    "profile_enable": (C.c_int, [_VP, C.c_int]),
+    "profile_read": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 PRODUCT_API_NAMES = tuple(_PRODUCT_SIGS)
 
@@ -120,6 +122,18 @@ class Hierarchy(FlatHierarchy):
 
     def synchronize(self):
         self._chk(self.f.synchronize(self.h), "synchronize")
+
+    KERNEL_KINDS = ("sc_forward", "sc_learn", "pred_step", "actor_forward", "actor_learn")
+
+    def profileEnable(self, on: bool = True):
+        self._chk(self.f.profile_enable(self.h, int(on)), "profile_enable")
+
+    def profileRead(self) -> dict:
+        """{kind: (device ms, launches)} accumulated since profileEnable()."""
+        ms = (C.c_double * 5)()
+        n = (C.c_int64 * 5)()
+        self._chk(self.f.profile_read(self.h, ms, n), "profile_read")
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNEL_KINDS)}
 
     def takeSCUpdateCount(self, l: int) -> int:
         return int(self.f.take_sc_update_count(self.h, l))
