@@ -51,6 +51,10 @@ public:
     void getReconstructions(int i, FloatBuffer &out) const;
     // (hidden column, visible column) pairs rewritten by learn since the counter was last read (algorithmic write bytes).
     unsigned long long takeUpdateCount();
+    // Test helpers: number of weights of visible layer i whose two device copies (F and R layout) differ, and the
+    // weights of one hidden column in the reference's CSR order [hz][slot][vz].
+    unsigned long long debugFRMismatch(int i) const;
+    void getColumnWeights(int i, int ox, int oy, std::vector<float> &out) const;
 
     // Ensemble support: member 0 allocates room for `batch` lock-stepped copies, every member draws its own weights.
     void initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize, const std::vector<VisibleLayerDesc> &visibleLayerDescs,

@@ -56,6 +56,11 @@ uint64_t ogn_take_sc_update_count(void *h, int l);
 int ogn_profile_enable(void *h, int on);
 int ogn_profile_read(void *h, double *ms, int64_t *launches);
 int ogn_device_count(void);
+/* Test helpers. fr_mismatch: number of SparseCoder weights whose F and R copies differ (must be 0; synchronises).
+ * column_weights: the weights of ONE hidden column (ox, oy) of SparseCoder l (kind 0), visible layer vli, in the
+ * reference's CSR order [hz][slot][vz]; returns the count. Lets a host check sizes the oracle cannot build. */
+int64_t ogn_debug_sc_fr_mismatch(void *h, int l, int vli);
+int64_t ogn_debug_column_weights(void *h, int kind, int l, int vli, int ox, int oy, float *out, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -276,6 +276,22 @@ int ogn_profile_read(void *hh, double *ms, int64_t *launches) {
         }
     });
 }
+// --- debug / test helpers (declared in ogn_b200.h) ---------------------------------------------------------------
+int64_t ogn_debug_sc_fr_mismatch(void *hh, int l, int vli) {
+    int64_t n = -1;
+    guard([&] { n = (int64_t)((Handle *)hh)->h.getSCLayer(l).debugFRMismatch(vli); });
+    return n;
+}
+int64_t ogn_debug_column_weights(void *hh, int kind, int l, int vli, int ox, int oy, float *out, int64_t cap) {
+    int64_t n = -1;
+    guard([&] {
+        std::vector<float> w;
+        if (kind == 0) ((Handle *)hh)->h.getSCLayer(l).getColumnWeights(vli, ox, oy, w);
+        else throw std::runtime_error("ogn_debug_column_weights: kind must be 0 (SparseCoder)");
+        n = weightsOut(w, out, cap);
+    });
+    return n;
+}
 int ogn_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

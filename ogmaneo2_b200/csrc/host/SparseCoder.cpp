@@ -181,6 +181,37 @@ const SparseCoder::VisibleLayer &SparseCoder::getVisibleLayer(int i) const {
     return vl;
 }
 
+unsigned long long SparseCoder::debugFRMismatch(int i) const {
+    DeviceContext &ctx = *impl->ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    const WeightSet &w = impl->ws.sets[i];
+    const ogn_wset d = w.desc();
+    DevBuf<unsigned long long> cnt;
+    cnt.allocZero(1, ctx.stream);
+    unsigned long long total = 0;
+    for (int m = 0; m < impl->batch; m++) kernelCheck(ogn_weights_fr_mismatch(&d, &w.geo->host, m, cnt.ptr(), ctx.stream), "fr_mismatch");
+    cnt.download(&total, 1, ctx.stream);
+    ctx.sync();
+    return total;
+}
+
+void SparseCoder::getColumnWeights(int i, int ox, int oy, std::vector<float> &out) const {
+    DeviceContext &ctx = *impl->ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    const WeightSet &w = impl->ws.sets[i];
+    const Geometry &g = *w.geo;
+    if (ox < w.fx0 || ox >= w.fx1) throw std::out_of_range("ogmaneo-b200: column not stored on this device");
+    const int64_t n = (int64_t)g.slots(ox, oy) * g.Vz * g.Hz, base = g.colBlock(ox, oy);
+    const ogn_wset d = w.desc();
+    DevBuf<float> stage;
+    stage.alloc((size_t)n);
+    const int col = oy + ox * g.Hy;
+    kernelCheck(ogn_weights_to_csr(&d, &g.host, 0, 0, col, col + 1, stage.ptr(), base, ctx.stream), "weights_to_csr");
+    out.resize((size_t)n);
+    stage.download(out.data(), (size_t)n, ctx.stream);
+    ctx.sync();
+}
+
 unsigned long long SparseCoder::takeUpdateCount() {
     cudaCheck(cudaSetDevice(impl->ctx->device), "cudaSetDevice");
     unsigned long long v = 0;
