@@ -48,6 +48,7 @@ typedef struct ogn_rf {
     const int *ngr, *pyr;     /* [Hy] R: number of visible-y groups (iy/pr) the field touches, prefix sum */
     const int *rlox, *rhix;   /* [Vx] first / last hidden x whose field covers visible x (rlox > rhix: none) */
     const int *rloy, *rhiy;   /* [Vy] */
+    int max_nx, max_nyf;      /* largest nx[] / nyf[] entry: bounds the slot descriptors of the 128-bit kernels */
 } ogn_rf;
 
 /* ---- per-launch descriptors, all passed BY VALUE (kernel parameter space): a launch never chases a descriptor
@@ -82,6 +83,11 @@ typedef struct ogn_learn_args {   /* visible layers of one launch share the geom
     ogn_learn_vl vl[OGN_MAX_VL];
     int nvl;
     int fx0, fx1;                 /* hidden x range whose F copy is stored on this device */
+    /* work list of the two-kernel learn (reconstruction, then update of the listed visible columns): room for
+     * batch * nvl * (vx1 - vx0) * Vy entries of 8 bytes, and two zero-initialised counters {entries, warps done} that
+     * the update kernel leaves at zero again. NULL selects the single fused kernel. */
+    void *work;
+    unsigned *work_counters;
 } ogn_learn_args;
 
 #define OGN_MAX_PRED_VL 8
@@ -131,7 +137,9 @@ int ogn_sc_forward(const ogn_fwd_args *args_host, int Hx, int Hy, int Hz, int x0
 
 /* K3 — SparseCoder::learn (SparseCoder.cpp:45-83) + multiplyOHVsT/countT/deltaChangedOHVsT (SparseMatrix.cpp:278-294,
  * 215-221, 572-590) for the visible layers in args (same geometry) and visible x in [vx0,vx1). update_count (optional)
- * is incremented by the number of (hidden column, visible column) pairs whose Vz weights were rewritten. */
+ * is incremented by the number of (hidden column, visible column) pairs whose Vz weights were rewritten.
+ * With Vz in {8,16,32} and a work list in args this is two launches: the reconstruction + arg-max over every visible
+ * column (a pure 128-bit gather), then the delta rule over the listed columns only. */
 int ogn_sc_learn(const ogn_learn_args *args_host, const int *hidden_cs, const int *hidden_cs_prev, int vx0, int vx1,
                  float alpha, int batch, unsigned long long *update_count, void *stream);
 

@@ -26,7 +26,7 @@ HOST_SOURCES = ["Device", "Helpers", "SparseCoder", "Predictor", "Actor", "Hiera
 
 
 def _sources():
-    srcs = [os.path.join(CSRC, "ogn_kernels.cu"), os.path.join(CSRC, "ogn_libm.h")]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     srcs += [os.path.join(CSRC, "host", f) for f in os.listdir(os.path.join(CSRC, "host"))]
     srcs += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include")) if f.endswith(".h")]
     srcs += [os.path.join(ROOT, "include", "ogmaneo", f) for f in os.listdir(os.path.join(ROOT, "include", "ogmaneo"))]

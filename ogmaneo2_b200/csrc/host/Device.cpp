@@ -115,6 +115,8 @@ void Geometry::build(const Int3 &hidden, const Int3 &visible, int r) {
     host.lox = t + o0; host.nx = t + o1; host.px = t + o2; host.loy = t + o3; host.ny = t + o4; host.py = t + o5;
     host.rlox = t + o6; host.rhix = t + o7; host.rloy = t + o8; host.rhiy = t + o9;
     host.loyf = t + o10; host.nyf = t + o11; host.pyf = t + o12; host.ngr = t + o13; host.pyr = t + o14;
+    host.max_nx = nx.empty() ? 0 : *std::max_element(nx.begin(), nx.end());
+    host.max_nyf = nyf.empty() ? 0 : *std::max_element(nyf.begin(), nyf.end());
 }
 
 std::shared_ptr<Geometry> Geometry::get(const Int3 &hidden, const Int3 &visible, int radius) {

@@ -19,6 +19,9 @@ struct SparseCoder::Impl {
     int cur = 0;
     bool prevAliasesCur = true;
     detail::DevBuf<unsigned long long> upd;
+    // work list of the two-kernel learn: visible columns whose reconstruction missed (8-byte entries) + {entries, warps done}
+    detail::DevBuf<unsigned long long> work;
+    detail::DevBuf<unsigned> workCounters;
     std::vector<detail::DevBuf<int>> inStage; // standalone step(): uploaded inputs
     // host-mirror validity
     bool csDirty = true, reconDirty = true;

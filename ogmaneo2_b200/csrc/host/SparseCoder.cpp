@@ -1,6 +1,8 @@
 // csrc/host/SparseCoder.cpp — ogmaneo::SparseCoder on the device (public interface: include/ogmaneo/SparseCoder.h).
 #include "LayerImpl.h"
 
+#include <algorithm>
+
 namespace ogmaneo {
 using namespace detail;
 
@@ -23,6 +25,8 @@ SparseCoder &SparseCoder::operator=(const SparseCoder &o) {
         impl->ws.cloneFrom(ctx, o.impl->ws);
         impl->cs_[0].cloneFrom(o.impl->cs_[0], ctx.stream); impl->cs_[1].cloneFrom(o.impl->cs_[1], ctx.stream);
         impl->upd.allocZero(1, ctx.stream);
+        impl->work.alloc(o.impl->work.size());
+        impl->workCounters.allocZero(2, ctx.stream);
         impl->inStage.resize(o.impl->inStage.size());
         ctx.sync();
     }
@@ -39,6 +43,17 @@ void SparseCoder::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, const st
     const size_t ncols = (size_t)hidden.x * hidden.y * batch;
     cs_[0].allocZero(ncols, ctx->stream); cs_[1].allocZero(ncols, ctx->stream);
     upd.allocZero(1, ctx->stream);
+    {   // one learn launch covers a run of equally-shaped visible layers: size the list for the largest run
+        size_t need = 0, v = 0;
+        while (v < vlds.size()) {
+            size_t e = v + 1;
+            while (e < vlds.size() && ws.sets[e].geo == ws.sets[v].geo) e++;
+            need = std::max(need, (e - v) * (size_t)(ws.sets[v].vx1 - ws.sets[v].vx0) * vlds[v].size.y * batch);
+            v = e;
+        }
+        work.alloc(std::max<size_t>(need, 1));
+        workCounters.allocZero(2, ctx->stream);
+    }
     inStage.clear(); inStage.resize(vlds.size());
     cur = 0; prevAliasesCur = true;
     csDirty = true; reconDirty = true; wDirty.assign(vlds.size(), 1);
@@ -102,6 +117,7 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
             ogn_learn_args la;
             std::memset(&la, 0, sizeof(la));
             la.geo = w0.geo->host; la.nvl = e - v; la.fx0 = w0.fx0; la.fx1 = w0.fx1;
+            la.work = m.work.ptr(); la.work_counters = m.workCounters.ptr();
             for (int k = v; k < e; k++) {
                 consumeKernel2(cs, visibleLayerDescs[k].size.x, visibleLayerDescs[k].size.y);
                 const WeightSet &w = m.ws.sets[k];

@@ -13,6 +13,8 @@
 // the reference's first-max-wins tie-break.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/ogn_kernels_api.h"
 #include "ogn_libm.h"
@@ -68,7 +70,6 @@ struct PackCtx {
     int dlo, dn;               // this lane's column covers dyU in [dlo, dlo + dn); dn == 0: lane has no column
     long long blk;             // F block offset of the pack
 };
-template <int G>
 __device__ __forceinline__ PackCtx pack_ctx(const ogn_rf &rf, int ox, int q, int p) {
     PackCtx c;
     c.lx = __ldg(rf.lox + ox);
@@ -183,7 +184,7 @@ k_sc_forward(const __grid_constant__ ogn_fwd_args A, int Hx, int Hy, int Hz, int
         for (int v = 0; v < A.nvl; ++v) {
             const ogn_fwd_vl &vl = A.vl[v];
             const ogn_rf &rf = A.geo[vl.geo];
-            const PackCtx c = pack_ctx<G>(rf, ox, q, p);
+            const PackCtx c = pack_ctx(rf, ox, q, p);
             const float *w = vl.wf + (c.blk + (long long)member * vl.mstride) + p * Hz + hcl;
             const int *cs = vl.cs + (long long)member * rf.Vx * rf.Vy;
             sum += gather_pack<G, true>(gm, gl, w, cs, c, rf.Vy, rf.Vz, P * Hz);
@@ -396,7 +397,7 @@ k_pred_step(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int Hz, int
             for (int v = 0; v < A.nvl; ++v) {
                 const ogn_pred_vl &vl = A.vl[v];
                 const ogn_rf &rf = A.geo[vl.geo];
-                const PackCtx c = pack_ctx<G>(rf, ox, q, p);
+                const PackCtx c = pack_ctx(rf, ox, q, p);
                 float *w = vl.wf + (c.blk + (long long)member * vl.mstride) + p * Hz + hcl;
                 const int *cs = vl.cs_prev + (long long)member * rf.Vx * rf.Vy;
                 delta_pack<G>(gm, gl, act, w, cs, delta, c, rf.Vy, rf.Vz, P * Hz);
@@ -416,7 +417,7 @@ k_pred_step(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int Hz, int
         for (int v = 0; v < A.nvl; ++v) {
             const ogn_pred_vl &vl = A.vl[v];
             const ogn_rf &rf = A.geo[vl.geo];
-            const PackCtx c = pack_ctx<G>(rf, ox, q, p);
+            const PackCtx c = pack_ctx(rf, ox, q, p);
             const float *w = vl.wf + (c.blk + (long long)member * vl.mstride) + p * Hz + hcl;
             const int *cs = vl.cs + (long long)member * rf.Vx * rf.Vy;
             sum += gather_pack<G, false>(gm, gl, w, cs, c, rf.Vy, rf.Vz, P * Hz);
@@ -489,7 +490,7 @@ __device__ __forceinline__ void actor_action_acts(unsigned gm, unsigned sm, int 
         float sum = 0.0f;
         for (int v = 0; v < A.nvl; ++v) {
             const ogn_rf &rf = A.geo[A.vl[v].geo_a];
-            const PackCtx c = pack_ctx<G>(rf, ox, q, p);
+            const PackCtx c = pack_ctx(rf, ox, q, p);
             const float *w = A.vl[v].wa + c.blk + p * Hz + hcl;
             sum += gather_pack<G, false>(gm, gl, w, A.vl[v].cs, c, rf.Vy, rf.Vz, P * Hz);
         }
@@ -588,12 +589,14 @@ k_actor_learn(const __grid_constant__ ogn_actor_args A, int Hx, int Hy, int Hz, 
                     ((hc == target ? 1.0f : 0.0f) - __ldcg(acts + hc) / fmaxf(0.0001f, total));
         for (int v = 0; v < A.nvl; ++v) {
             const ogn_rf &rf = A.geo[A.vl[v].geo_a];
-            const PackCtx c = pack_ctx<G>(rf, ox, q, p);
+            const PackCtx c = pack_ctx(rf, ox, q, p);
             float *w = A.vl[v].wa + c.blk + p * Hz + hcl;
             delta_pack<G>(gm, gl, act, w, A.vl[v].cs, delta, c, rf.Vy, rf.Vz, P * Hz);
         }
     }
 }
+
+#include "ogn_vec.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // Weight (re)layout, init and checks. One block per hidden column; threads walk the column's CSR-order elements
@@ -702,6 +705,15 @@ inline int group_lanes(int z) {
     return g;
 }
 inline int launch_status() { return (int)cudaGetLastError(); }
+inline int update_grid_blocks() { // resident blocks of the persistent update kernel: 8 blocks of 256 threads per SM
+    static int n = 0;
+    if (!n) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        n = sms * 8;
+    }
+    return n;
+}
 
 #define OGN_DISPATCH_G(G_, CALL)                 \
     switch (G_) {                                \
@@ -721,16 +733,53 @@ const char *ogn_cuda_error_string(int code) { return cudaGetErrorString((cudaErr
 
 static inline int pack_factor(int g) { return g >= 8 ? 32 / g : 4; }
 
+// The 128-bit kernels (ogn_vec.cuh) apply when a row holds 8, 16 or 32 cells and the slot descriptors fit their bit fields.
+static inline bool vec_row(int z) { return z == 8 || z == 16 || z == 32; }
+static inline bool vec_geo(const ogn_rf &g) {
+    return (long long)g.max_nx * g.max_nyf * g.Vz < (1ll << 20) && g.max_nyf < 0xFFF && g.max_nx > 0 && g.max_nyf > 0;
+}
+// OGN_KERNELS: "scalar" forces the generic one-cell-per-lane kernels; "vec1"/"vec2" pick the loads-in-flight depth of the
+// 128-bit kernels (8 or 16 line loads per lane before the first add). Default vec2.
+static int kernel_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("OGN_KERNELS");
+        v = 2;
+        if (e && !strcmp(e, "scalar")) v = 0;
+        else if (e && !strcmp(e, "vec1")) v = 1;
+    }
+    return v;
+}
+
+#define OGN_DISPATCH_Z(Z_, CALL)                     \
+    switch (Z_) {                                    \
+    case 8: { constexpr int Z = 8; CALL; } break;    \
+    case 16: { constexpr int Z = 16; CALL; } break;  \
+    default: { constexpr int Z = 32; CALL; } break;  \
+    }
+
 int ogn_sc_forward(const ogn_fwd_args *args, int Hx, int Hy, int Hz, int x0, int x1, int batch, int *hidden_cs, int *hidden_cs2,
                    void *stream) {
     if (args->nvl > OGN_MAX_VL) return (int)cudaErrorInvalidValue;
     if (x1 <= x0 || batch <= 0 || Hy <= 0) return 0;
     const int g = group_lanes(Hz), P = pack_factor(g), ppr = (Hy + P - 1) / P, npacks = (x1 - x0) * ppr;
-    for (int v = 0; v < args->nvl; v++)
+    bool vecOk = vec_row(Hz) && kernel_variant() > 0;
+    for (int v = 0; v < args->nvl; v++) {
         if (args->geo[args->vl[v].geo].pf != P) return (int)cudaErrorInvalidValue;
+        vecOk = vecOk && vec_geo(args->geo[args->vl[v].geo]);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vecOk) {
+        dim3 grid((unsigned)(((long long)npacks * 8 + kThreads - 1) / kThreads), (unsigned)batch);
+        if (kernel_variant() == 1) {
+            OGN_DISPATCH_Z(Hz, (vec::k_sc_forward_v<Z, 1><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, hidden_cs, hidden_cs2)));
+        } else {
+            OGN_DISPATCH_Z(Hz, (vec::k_sc_forward_v<Z, 2><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, hidden_cs, hidden_cs2)));
+        }
+        return launch_status();
+    }
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);
-    OGN_DISPATCH_G(g, (k_sc_forward<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, x0, npacks, ppr, hidden_cs,
-                                                                                 hidden_cs2)));
+    OGN_DISPATCH_G(g, (k_sc_forward<G><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, Hz, x0, npacks, ppr, hidden_cs, hidden_cs2)));
     return launch_status();
 }
 
@@ -740,9 +789,29 @@ int ogn_sc_learn(const ogn_learn_args *args, const int *hidden_cs, const int *hi
     if (args->nvl > OGN_MAX_VL) return (int)cudaErrorInvalidValue;
     const int g = group_lanes(args->geo.Vz), P = pack_factor(g), ppr = (args->geo.Vy + P - 1) / P, npacks = (vx1 - vx0) * ppr;
     if (args->geo.pr != P) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec_row(args->geo.Vz) && kernel_variant() > 0 && args->work && args->work_counters) {
+        const int Vz = args->geo.Vz;
+        dim3 grid((unsigned)(((long long)npacks * 8 + kThreads - 1) / kThreads), (unsigned)batch, (unsigned)args->nvl);
+        int2 *work = (int2 *)args->work;
+        unsigned *cnt = args->work_counters;
+        if (kernel_variant() == 1) {
+            OGN_DISPATCH_Z(Vz, (vec::k_sc_recon_v<Z, 1><<<grid, kThreads, 0, st>>>(*args, hidden_cs, vx0, npacks, ppr, work, cnt)));
+        } else {
+            OGN_DISPATCH_Z(Vz, (vec::k_sc_recon_v<Z, 2><<<grid, kThreads, 0, st>>>(*args, hidden_cs, vx0, npacks, ppr, work, cnt)));
+        }
+        int e = launch_status();
+        if (e) return e;
+        // persistent grid over the work list: enough warps to fill the machine, never more than one per possible entry
+        long long maxEntries = (long long)(vx1 - vx0) * args->geo.Vy * batch * args->nvl;
+        long long blocks = (maxEntries + (kThreads / 32) - 1) / (kThreads / 32);
+        if (blocks > update_grid_blocks()) blocks = update_grid_blocks();
+        OGN_DISPATCH_Z(Vz, (vec::k_sc_update_v<Z><<<(unsigned)blocks, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, work, cnt, cnt + 1,
+                                                                                      alpha, update_count)));
+        return launch_status();
+    }
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch, (unsigned)args->nvl);
-    OGN_DISPATCH_G(g, (k_sc_learn<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, hidden_cs, hidden_cs_prev, vx0, npacks, ppr, alpha,
-                                                                               update_count)));
+    OGN_DISPATCH_G(g, (k_sc_learn<G><<<grid, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, vx0, npacks, ppr, alpha, update_count)));
     return launch_status();
 }
 
@@ -751,11 +820,26 @@ int ogn_pred_step(const ogn_pred_args *args, int Hx, int Hy, int Hz, int x0, int
     if (args->nvl > OGN_MAX_PRED_VL) return (int)cudaErrorInvalidValue;
     if (x1 <= x0 || batch <= 0 || Hy <= 0) return 0;
     const int g = group_lanes(Hz), P = pack_factor(g), ppr = (Hy + P - 1) / P, npacks = (x1 - x0) * ppr;
-    for (int v = 0; v < args->nvl; v++)
+    bool vecOk = vec_row(Hz) && kernel_variant() > 0;
+    for (int v = 0; v < args->nvl; v++) {
         if (args->geo[args->vl[v].geo].pf != P) return (int)cudaErrorInvalidValue;
+        vecOk = vecOk && vec_geo(args->geo[args->vl[v].geo]);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vecOk) {
+        dim3 grid((unsigned)(((long long)npacks * 8 + kThreads - 1) / kThreads), (unsigned)batch);
+        if (kernel_variant() == 1) {
+            OGN_DISPATCH_Z(Hz, (vec::k_pred_step_v<Z, 1><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, learn, activate, target_cs,
+                                                                                 alpha, activations, hidden_cs)));
+        } else {
+            OGN_DISPATCH_Z(Hz, (vec::k_pred_step_v<Z, 2><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, learn, activate, target_cs,
+                                                                                 alpha, activations, hidden_cs)));
+        }
+        return launch_status();
+    }
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);
-    OGN_DISPATCH_G(g, (k_pred_step<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, x0, npacks, ppr, learn, activate,
-                                                                                target_cs, alpha, activations, hidden_cs)));
+    OGN_DISPATCH_G(g, (k_pred_step<G><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, Hz, x0, npacks, ppr, learn, activate, target_cs, alpha,
+                                                              activations, hidden_cs)));
     return launch_status();
 }
 
