@@ -357,9 +357,13 @@ def main():
     for (l, kind, b, per_pair) in sites:
         a = alg.setdefault(kind, 0.0)
         alg[kind] = a + b * counts[l] / max(world, 1)  # bytes one rank moves (x-slab sharding splits every launch)
-    if "sc_learn" in alg:
-        alg["sc_learn"] += sum(u * 4 * cfg["inputSizes"][0][2] if l == 0 else u * 4 * cfg["layerDescs"][l - 1].hiddenSize[2]
-                               for l, u in enumerate(upd))
+    # data-dependent SC writes (4 B x Vz per rewritten pair): the update kernel's bytes when learn ran as two kernels
+    upd_bytes = sum(u * 4 * cfg["inputSizes"][0][2] if l == 0 else u * 4 * cfg["layerDescs"][l - 1].hiddenSize[2]
+                    for l, u in enumerate(upd))
+    if prof.get("sc_update", (0.0, 0))[1] > 0:
+        alg["sc_update"] = upd_bytes
+    elif "sc_learn" in alg:
+        alg["sc_learn"] += upd_bytes
     kernels = {}
     for kind, (kms, n) in prof.items():
         if n == 0:

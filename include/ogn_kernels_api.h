@@ -49,6 +49,7 @@ typedef struct ogn_rf {
     const int *rlox, *rhix;   /* [Vx] first / last hidden x whose field covers visible x (rlox > rhix: none) */
     const int *rloy, *rhiy;   /* [Vy] */
     int max_nx, max_nyf;      /* largest nx[] / nyf[] entry: bounds the slot descriptors of the 128-bit kernels */
+    int max_cov;              /* largest number of hidden columns covering one visible column */
 } ogn_rf;
 
 /* ---- per-launch descriptors, all passed BY VALUE (kernel parameter space): a launch never chases a descriptor
@@ -139,9 +140,15 @@ int ogn_sc_forward(const ogn_fwd_args *args_host, int Hx, int Hy, int Hz, int x0
  * 215-221, 572-590) for the visible layers in args (same geometry) and visible x in [vx0,vx1). update_count (optional)
  * is incremented by the number of (hidden column, visible column) pairs whose Vz weights were rewritten.
  * With Vz in {8,16,32} and a work list in args this is two launches: the reconstruction + arg-max over every visible
- * column (a pure 128-bit gather), then the delta rule over the listed columns only. */
+ * column (a pure 128-bit gather), then the delta rule over the listed columns only.
+ * phase selects what is queued: OGN_LEARN_ALL, or the two halves separately (so that a caller can time them). When
+ * ogn_sc_learn_is_split() is 0 the fused kernel runs in the RECONSTRUCT phase and UPDATE queues nothing. */
+#define OGN_LEARN_ALL 0
+#define OGN_LEARN_RECONSTRUCT 1
+#define OGN_LEARN_UPDATE 2
 int ogn_sc_learn(const ogn_learn_args *args_host, const int *hidden_cs, const int *hidden_cs_prev, int vx0, int vx1,
-                 float alpha, int batch, unsigned long long *update_count, void *stream);
+                 float alpha, int batch, unsigned long long *update_count, int phase, void *stream);
+int ogn_sc_learn_is_split(const ogn_learn_args *args_host);
 
 /* K6+K7+K8 — Predictor::learn (Predictor.cpp:49-70, deltaOHVs SparseMatrix.cpp:488-501), then Predictor::forward
  * (Predictor.cpp:13-47), then inputCs -> inputCsPrev (Predictor.cpp:118-126), over hidden x in [x0,x1).

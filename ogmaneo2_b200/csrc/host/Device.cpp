@@ -117,6 +117,10 @@ void Geometry::build(const Int3 &hidden, const Int3 &visible, int r) {
     host.loyf = t + o10; host.nyf = t + o11; host.pyf = t + o12; host.ngr = t + o13; host.pyr = t + o14;
     host.max_nx = nx.empty() ? 0 : *std::max_element(nx.begin(), nx.end());
     host.max_nyf = nyf.empty() ? 0 : *std::max_element(nyf.begin(), nyf.end());
+    int mcx = 0, mcy = 0;
+    for (int i = 0; i < Vx; i++) mcx = std::max(mcx, rhix[i] - rlox[i] + 1);
+    for (int i = 0; i < Vy; i++) mcy = std::max(mcy, rhiy[i] - rloy[i] + 1);
+    host.max_cov = std::max(mcx, 0) * std::max(mcy, 0);
 }
 
 std::shared_ptr<Geometry> Geometry::get(const Int3 &hidden, const Int3 &visible, int radius) {

@@ -22,7 +22,7 @@ namespace detail {
 void cudaCheck(cudaError_t e, const char *what);
 inline void kernelCheck(int code, const char *what) { cudaCheck((cudaError_t)code, what); }
 
-enum KernelKind { kScForward = 0, kScLearn = 1, kPredStep = 2, kActorForward = 3, kActorLearn = 4, kKernelKinds = 5 };
+enum KernelKind { kScForward = 0, kScLearn = 1, kPredStep = 2, kActorForward = 3, kActorLearn = 4, kScUpdate = 5, kKernelKinds = 6 };
 
 // One device + one stream. Created lazily by ComputeSystem::context(); throws if no sm_100 device is usable.
 struct DeviceContext {
@@ -35,8 +35,8 @@ struct DeviceContext {
     // Launch accounting: counts are always kept; with profiling on, every launch is bracketed by two CUDA events on
     // `stream` and profileCollect() (after a sync) turns them into per-kind device time.
     bool profiling = false;
-    long long launches[kKernelKinds] = {0, 0, 0, 0, 0};
-    double kernelMs[kKernelKinds] = {0, 0, 0, 0, 0};
+    long long launches[kKernelKinds] = {0, 0, 0, 0, 0, 0};
+    double kernelMs[kKernelKinds] = {0, 0, 0, 0, 0, 0};
     struct Rec { cudaEvent_t a, b; int kind; };
     std::vector<Rec> recs;
     std::vector<cudaEvent_t> eventPool;

@@ -125,8 +125,15 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
                 l.wf = w.fBase(); l.wr = w.rBase(); l.recon = w.recon.ptr(); l.cs = inputCsDev[k];
                 l.f_mstride = w.fCount(); l.r_mstride = w.rCount();
             }
+            // reconstruction (or the whole fused learn when the 128-bit path does not apply), then the work-list update
             { LaunchScope ls(ctx, kScLearn);
-            kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), ctx.stream), "sc_learn"); }
+            kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_RECONSTRUCT, ctx.stream),
+                        "sc_learn"); }
+            if (ogn_sc_learn_is_split(&la)) {
+                LaunchScope ls(ctx, kScUpdate);
+                kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_UPDATE, ctx.stream),
+                            "sc_update");
+            }
             v = e;
         }
         std::fill(m.wDirty.begin(), m.wDirty.end(), 1);

@@ -739,17 +739,28 @@ static inline bool vec_geo(const ogn_rf &g) {
     return (long long)g.max_nx * g.max_nyf * g.Vz < (1ll << 20) && g.max_nyf < 0xFFF && g.max_nx > 0 && g.max_nyf > 0;
 }
 // OGN_KERNELS: "scalar" forces the generic one-cell-per-lane kernels; "vec1"/"vec2" pick the loads-in-flight depth of the
-// 128-bit kernels (8 or 16 line loads per lane before the first add). Default vec2.
+// 128-bit kernels (8 or 16 line loads per lane before the first add). Default vec1 (measured: profiles/README.md).
 static int kernel_variant() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("OGN_KERNELS");
-        v = 2;
+        v = 1;
         if (e && !strcmp(e, "scalar")) v = 0;
-        else if (e && !strcmp(e, "vec1")) v = 1;
+        else if (e && !strcmp(e, "vec2")) v = 2;
     }
     return v;
 }
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static int vec_threads() { // experiment knob: threads per block of the 128-bit kernels (a multiple of 32, at most 256)
+    static int v = 0;
+    if (!v) { v = env_int("OGN_VEC_THREADS", kThreads); if (v < 32 || v > kThreads || v % 32) v = kThreads; }
+    return v;
+}
+static int pred_minb() { static int v = -1; if (v < 0) v = env_int("OGN_PRED_MINB", 1); return v; }
 
 #define OGN_DISPATCH_Z(Z_, CALL)                     \
     switch (Z_) {                                    \
@@ -770,11 +781,12 @@ int ogn_sc_forward(const ogn_fwd_args *args, int Hx, int Hy, int Hz, int x0, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (vecOk) {
-        dim3 grid((unsigned)(((long long)npacks * 8 + kThreads - 1) / kThreads), (unsigned)batch);
+        const int vt = vec_threads();
+        dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
         if (kernel_variant() == 1) {
-            OGN_DISPATCH_Z(Hz, (vec::k_sc_forward_v<Z, 1><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, hidden_cs, hidden_cs2)));
+            OGN_DISPATCH_Z(Hz, (vec::k_sc_forward_v<Z, 1><<<grid, vt, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, hidden_cs, hidden_cs2)));
         } else {
-            OGN_DISPATCH_Z(Hz, (vec::k_sc_forward_v<Z, 2><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, hidden_cs, hidden_cs2)));
+            OGN_DISPATCH_Z(Hz, (vec::k_sc_forward_v<Z, 2><<<grid, vt, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, hidden_cs, hidden_cs2)));
         }
         return launch_status();
     }
@@ -783,33 +795,45 @@ int ogn_sc_forward(const ogn_fwd_args *args, int Hx, int Hy, int Hz, int x0, int
     return launch_status();
 }
 
+int ogn_sc_learn_is_split(const ogn_learn_args *args) {
+    return vec_row(args->geo.Vz) && kernel_variant() > 0 && args->work && args->work_counters;
+}
+
 int ogn_sc_learn(const ogn_learn_args *args, const int *hidden_cs, const int *hidden_cs_prev, int vx0, int vx1, float alpha, int batch,
-                 unsigned long long *update_count, void *stream) {
+                 unsigned long long *update_count, int phase, void *stream) {
     if (vx1 <= vx0 || batch <= 0 || args->nvl <= 0) return 0;
     if (args->nvl > OGN_MAX_VL) return (int)cudaErrorInvalidValue;
     const int g = group_lanes(args->geo.Vz), P = pack_factor(g), ppr = (args->geo.Vy + P - 1) / P, npacks = (vx1 - vx0) * ppr;
     if (args->geo.pr != P) return (int)cudaErrorInvalidValue;
     cudaStream_t st = (cudaStream_t)stream;
-    if (vec_row(args->geo.Vz) && kernel_variant() > 0 && args->work && args->work_counters) {
+    if (ogn_sc_learn_is_split(args)) {
         const int Vz = args->geo.Vz;
-        dim3 grid((unsigned)(((long long)npacks * 8 + kThreads - 1) / kThreads), (unsigned)batch, (unsigned)args->nvl);
+        const int vt = vec_threads();
+        dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch, (unsigned)args->nvl);
         int2 *work = (int2 *)args->work;
         unsigned *cnt = args->work_counters;
-        if (kernel_variant() == 1) {
-            OGN_DISPATCH_Z(Vz, (vec::k_sc_recon_v<Z, 1><<<grid, kThreads, 0, st>>>(*args, hidden_cs, vx0, npacks, ppr, work, cnt)));
-        } else {
-            OGN_DISPATCH_Z(Vz, (vec::k_sc_recon_v<Z, 2><<<grid, kThreads, 0, st>>>(*args, hidden_cs, vx0, npacks, ppr, work, cnt)));
+        if (phase != OGN_LEARN_UPDATE) {
+            if (kernel_variant() == 1) {
+                OGN_DISPATCH_Z(Vz, (vec::k_sc_recon_v<Z, 1><<<grid, vt, 0, st>>>(*args, hidden_cs, vx0, npacks, ppr, work, cnt)));
+            } else {
+                OGN_DISPATCH_Z(Vz, (vec::k_sc_recon_v<Z, 2><<<grid, vt, 0, st>>>(*args, hidden_cs, vx0, npacks, ppr, work, cnt)));
+            }
+            int e = launch_status();
+            if (e || phase == OGN_LEARN_RECONSTRUCT) return e;
         }
-        int e = launch_status();
-        if (e) return e;
-        // persistent grid over the work list: enough warps to fill the machine, never more than one per possible entry
-        long long maxEntries = (long long)(vx1 - vx0) * args->geo.Vy * batch * args->nvl;
-        long long blocks = (maxEntries + (kThreads / 32) - 1) / (kThreads / 32);
+        // persistent grid over the work units (chunks of 32/LC * 4 cover items of a listed column): enough warps to fill the
+        // machine, never more than one per possible unit
+        const int itemsPerUnit = (32 / (Vz / 4)) * 4;
+        const int chunks = (args->geo.max_cov + itemsPerUnit - 1) / itemsPerUnit;
+        if (chunks <= 0) return 0;
+        long long maxUnits = (long long)(vx1 - vx0) * args->geo.Vy * batch * args->nvl * chunks;
+        long long blocks = (maxUnits + (kThreads / 32) - 1) / (kThreads / 32);
         if (blocks > update_grid_blocks()) blocks = update_grid_blocks();
         OGN_DISPATCH_Z(Vz, (vec::k_sc_update_v<Z><<<(unsigned)blocks, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, work, cnt, cnt + 1,
-                                                                                      alpha, update_count)));
+                                                                                      alpha, update_count, chunks)));
         return launch_status();
     }
+    if (phase == OGN_LEARN_UPDATE) return 0;
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch, (unsigned)args->nvl);
     OGN_DISPATCH_G(g, (k_sc_learn<G><<<grid, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, vx0, npacks, ppr, alpha, update_count)));
     return launch_status();
@@ -827,14 +851,16 @@ int ogn_pred_step(const ogn_pred_args *args, int Hx, int Hy, int Hz, int x0, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (vecOk) {
-        dim3 grid((unsigned)(((long long)npacks * 8 + kThreads - 1) / kThreads), (unsigned)batch);
-        if (kernel_variant() == 1) {
-            OGN_DISPATCH_Z(Hz, (vec::k_pred_step_v<Z, 1><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, learn, activate, target_cs,
-                                                                                 alpha, activations, hidden_cs)));
-        } else {
-            OGN_DISPATCH_Z(Hz, (vec::k_pred_step_v<Z, 2><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, learn, activate, target_cs,
-                                                                                 alpha, activations, hidden_cs)));
-        }
+        const int vt = vec_threads();
+        dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
+#define OGN_PRED_V(NCH_, MINB_)                                                                                                      \
+    OGN_DISPATCH_Z(Hz, (vec::k_pred_step_v<Z, NCH_, MINB_><<<grid, vt, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, learn, activate, target_cs, \
+                                                                            alpha, activations, hidden_cs)))
+        if (kernel_variant() == 2) { OGN_PRED_V(2, 1); }
+        else if (pred_minb() == 3) { OGN_PRED_V(1, 3); }
+        else if (pred_minb() == 4) { OGN_PRED_V(1, 4); }
+        else { OGN_PRED_V(1, 1); }
+#undef OGN_PRED_V
         return launch_status();
     }
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads)
 k_sc_forward_v(const __grid_constant__ ogn_fwd_args A, int Hx, int Hy, int x0, int npacks, int packsPerRow, int *__restrict__ out0,
                int *__restrict__ out1) {
     const int sub = threadIdx.x & 7;
-    const int pack = (blockIdx.x * kThreads + threadIdx.x) >> 3;
+    const int pack = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     if (pack >= npacks) return; // whole octets leave together
     const unsigned om = octet_mask();
     const int member = blockIdx.y;
@@ -180,13 +180,13 @@ k_sc_forward_v(const __grid_constant__ ogn_fwd_args A, int Hx, int Hy, int x0, i
 // ---------------------------------------------------------------------------------------------------------------
 // K6+K7+K8: Predictor::learn (Predictor.cpp:49-70), Predictor::forward (:13-47), inputCs -> inputCsPrev (:118-126),
 // Hz = Z in {8, 16, 32}.
-template <int Z, int NCH>
-__global__ void __launch_bounds__(kThreads)
+template <int Z, int NCH, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 k_pred_step_v(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int x0, int npacks, int packsPerRow, int learn, int activate,
               const int *__restrict__ target, float alpha, float *acts, int *__restrict__ hiddenCs) {
     const int member = blockIdx.y;
     if (activate) { // K8: the grid copies the inputs into the *other* inputCsPrev buffer (never read by this launch)
-        const int tid = blockIdx.x * kThreads + threadIdx.x, nth = gridDim.x * kThreads;
+        const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
         for (int v = 0; v < A.nvl; ++v) {
             if (!A.vl[v].cs_prev_out) continue;
             const int n = A.geo[A.vl[v].geo].Vx * A.geo[A.vl[v].geo].Vy;
@@ -195,7 +195,7 @@ k_pred_step_v(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int x0, i
         }
     }
     const int sub = threadIdx.x & 7;
-    const int pack = (blockIdx.x * kThreads + threadIdx.x) >> 3;
+    const int pack = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     if (pack >= npacks) return;
     const unsigned om = octet_mask();
     const PackId id = pack_id<Z>(pack, packsPerRow, x0, Hy, sub);
@@ -278,7 +278,7 @@ k_sc_recon_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ h
              int2 *__restrict__ work, unsigned *workCount) {
     constexpr int PR = 32 / Z;
     const int sub = threadIdx.x & 7;
-    const int pack = (blockIdx.x * kThreads + threadIdx.x) >> 3;
+    const int pack = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     if (pack >= npacks) return;
     const unsigned om = octet_mask();
     const int member = blockIdx.y;
@@ -365,27 +365,73 @@ k_sc_recon_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ h
 }
 
 // K3, part 2: the delta rule on the weights of hidden columns whose state changed (deltaChangedOHVsT,
-// SparseMatrix.cpp:572-590; SparseCoder.cpp:72-81) for the visible columns on the work list. One warp per listed column,
-// LC = Z/4 lanes per (hidden column, visible column) pair, so 32/LC pairs are rewritten per warp instruction: the R copy
-// with one 128-bit read-modify-write, the F copy with four scalar stores (one per forward row). The last warp to finish
-// resets the list for the next launch.
+// SparseMatrix.cpp:572-590; SparseCoder.cpp:72-81) for the visible columns on the work list. A work unit is one chunk of
+// 32/LC * UN cover items of one listed column, one warp per unit; LC = Z/4 lanes per (hidden column, visible column)
+// pair, so 32/LC pairs are rewritten per warp instruction: the R copy with one 128-bit read-modify-write, the F copy with
+// four scalar stores (one per forward row; 16 partially written sectors per pair — the HBM cost of keeping two layouts,
+// measured in profiles/README.md: the kernel is DRAM-bound on those sector fills and write-backs, an L2 prefetch of the
+// sectors made it slower). The last warp to finish resets the list for the next launch.
+
 template <int Z>
 __global__ void __launch_bounds__(kThreads)
 k_sc_update_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ hcsAll, const int *__restrict__ hcsPrevAll,
-              const int2 *__restrict__ work, unsigned *workCount, unsigned *doneCount, float alpha, unsigned long long *updCount) {
+              const int2 *__restrict__ work, unsigned *workCount, unsigned *doneCount, float alpha, unsigned long long *updCount,
+              int chunksPerEntry) {
     constexpr int LC = Z / 4, IPW = 32 / LC, PR = 32 / Z, UN = 4;
     const ogn_rf &rf = A.geo;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
     const int it = lane / LC, vc0 = (lane % LC) * 4;
     const unsigned n = *(volatile unsigned *)workCount;
+    const unsigned long long nunits = (unsigned long long)n * (unsigned)chunksPerEntry;
+    const long long fstep = (long long)rf.pf * rf.Hz; // floats between the forward rows of consecutive visible cells
     int nupd = 0;
-    for (unsigned e = warp; e < n; e += nwarps) {
+    for (unsigned long long unit = warp; unit < nunits; unit += nwarps) {
+        const unsigned e = (unsigned)(unit / (unsigned)chunksPerEntry);
+        const int k0 = (int)(unit - (unsigned long long)e * (unsigned)chunksPerEntry) * (IPW * UN);
         const int2 wk = work[e];
+        const int vx = wk.y / rf.Vy, vy = wk.y - vx * rf.Vy;
+        const int hx0 = __ldg(rf.rlox + vx), hx1 = __ldg(rf.rhix + vx);
+        const int hy0 = __ldg(rf.rloy + vy), hy1 = __ldg(rf.rhiy + vy);
+        const int ncy = max(0, hy1 - hy0 + 1), ncov = max(0, hx1 - hx0 + 1) * ncy;
+        if (k0 >= ncov) continue;
         const int member = wk.x / A.nvl;
         const ogn_learn_vl &vl = A.vl[wk.x % A.nvl];
-        const int vx = wk.y / rf.Vy, vy = wk.y - vx * rf.Vy;
         const long long vcol = (long long)member * rf.Vx * rf.Vy + wk.y;
+        const int *hcs = hcsAll + (long long)member * rf.Hx * rf.Hy;
+        const int *hcsPrev = hcsPrevAll + (long long)member * rf.Hx * rf.Hy;
+        float *wr = vl.wr + (long long)member * vl.r_mstride + vc0;
+        float *wf = vl.wf + (long long)member * vl.f_mstride;
+
+        long long offR[UN], offF[UN];
+        int fl[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int k = k0 + u * IPW + it;
+            fl[u] = 0;
+            offR[u] = 0; offF[u] = 0;
+            if (k < ncov) {
+                const int ox = hx0 + k / ncy, oy = hy0 + k % ncy;
+                const int h = ox * rf.Hy + oy;
+                const int hc = __ldg(hcs + h);
+                if (hc != __ldg(hcsPrev + h)) {
+                    const int ylo = __ldg(rf.loy + oy);
+                    const int dx = vx - __ldg(rf.lox + ox);
+                    offR[u] = r_block(rf, ox, oy) +
+                              ((((long long)dx * __ldg(rf.ngr + oy) + (vy / PR - ylo / PR)) * rf.Hz + hc) * PR + (vy % PR)) * Z;
+                    const int qh = oy / rf.pf, ph = oy % rf.pf;
+                    offF[u] = f_block(rf, ox, qh) +
+                              (((long long)dx * __ldg(rf.nyf + qh) + (vy - __ldg(rf.loyf + qh))) * Z * rf.pf + ph) * rf.Hz + hc +
+                              (long long)vc0 * fstep;
+                    fl[u] = 1 | ((ox >= A.fx0 && ox < A.fx1) ? 2 : 0);
+                }
+            }
+        }
+        float4 w[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+            if (fl[u]) w[u] = ld_plain(wr + offR[u]);
+        // delta of this lane's 4 visible cells (SparseCoder.cpp:78) while the loads are in flight
         const int target = __ldg(vl.cs + vcol);
         const float4 r = ld_plain(vl.recon + vcol * Z + vc0);
         float4 delta;
@@ -393,56 +439,18 @@ k_sc_update_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ 
         delta.y = alpha * ((vc0 + 1 == target ? 1.0f : 0.0f) - ogn_expf(r.y));
         delta.z = alpha * ((vc0 + 2 == target ? 1.0f : 0.0f) - ogn_expf(r.z));
         delta.w = alpha * ((vc0 + 3 == target ? 1.0f : 0.0f) - ogn_expf(r.w));
-        const int *hcs = hcsAll + (long long)member * rf.Hx * rf.Hy;
-        const int *hcsPrev = hcsPrevAll + (long long)member * rf.Hx * rf.Hy;
-        float *wr = vl.wr + (long long)member * vl.r_mstride + vc0;
-        float *wf = vl.wf + (long long)member * vl.f_mstride;
-        const int hx0 = __ldg(rf.rlox + vx), hx1 = __ldg(rf.rhix + vx);
-        const int hy0 = __ldg(rf.rloy + vy), hy1 = __ldg(rf.rhiy + vy);
-        const int ncy = max(0, hy1 - hy0 + 1), ncov = max(0, hx1 - hx0 + 1) * ncy;
-        const long long fstep = (long long)rf.pf * rf.Hz; // floats between the forward rows of consecutive visible cells
-        for (int k0 = 0; k0 < ncov; k0 += IPW * UN) {
-            long long offR[UN], offF[UN];
-            float4 w[UN];
-            int fl[UN];
 #pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                const int k = k0 + u * IPW + it;
-                fl[u] = 0;
-                offR[u] = 0; offF[u] = 0;
-                if (k < ncov) {
-                    const int ox = hx0 + k / ncy, oy = hy0 + k % ncy;
-                    const int h = ox * rf.Hy + oy;
-                    const int hc = __ldg(hcs + h);
-                    if (hc != __ldg(hcsPrev + h)) {
-                        const int ylo = __ldg(rf.loy + oy);
-                        const int dx = vx - __ldg(rf.lox + ox);
-                        offR[u] = r_block(rf, ox, oy) +
-                                  ((((long long)dx * __ldg(rf.ngr + oy) + (vy / PR - ylo / PR)) * rf.Hz + hc) * PR + (vy % PR)) * Z;
-                        const int qh = oy / rf.pf, ph = oy % rf.pf;
-                        offF[u] = f_block(rf, ox, qh) +
-                                  (((long long)dx * __ldg(rf.nyf + qh) + (vy - __ldg(rf.loyf + qh))) * Z * rf.pf + ph) * rf.Hz + hc +
-                                  (long long)vc0 * fstep;
-                        fl[u] = 1 | ((ox >= A.fx0 && ox < A.fx1) ? 2 : 0);
-                    }
+        for (int u = 0; u < UN; ++u)
+            if (fl[u]) {
+                float4 nw = w[u];
+                nw.x += delta.x; nw.y += delta.y; nw.z += delta.z; nw.w += delta.w;
+                st_plain(wr + offR[u], nw);
+                if (fl[u] & 2) {
+                    float *f = wf + offF[u];
+                    f[0] = nw.x; f[fstep] = nw.y; f[2 * fstep] = nw.z; f[3 * fstep] = nw.w;
                 }
+                if (vc0 == 0) nupd++;
             }
-#pragma unroll
-            for (int u = 0; u < UN; ++u)
-                if (fl[u]) w[u] = ld_plain(wr + offR[u]);
-#pragma unroll
-            for (int u = 0; u < UN; ++u)
-                if (fl[u]) {
-                    float4 nw = w[u];
-                    nw.x += delta.x; nw.y += delta.y; nw.z += delta.z; nw.w += delta.w;
-                    st_plain(wr + offR[u], nw);
-                    if (fl[u] & 2) {
-                        float *f = wf + offF[u];
-                        f[0] = nw.x; f[fstep] = nw.y; f[2 * fstep] = nw.z; f[3 * fstep] = nw.w;
-                    }
-                    if (vc0 == 0) nupd++;
-                }
-        }
     }
     // bookkeeping: pairs rewritten, and the last warp out empties the list
 #pragma unroll

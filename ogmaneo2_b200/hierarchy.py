@@ -123,15 +123,15 @@ class Hierarchy(FlatHierarchy):
     def synchronize(self):
         self._chk(self.f.synchronize(self.h), "synchronize")
 
-    KERNEL_KINDS = ("sc_forward", "sc_learn", "pred_step", "actor_forward", "actor_learn")
+    KERNEL_KINDS = ("sc_forward", "sc_learn", "pred_step", "actor_forward", "actor_learn", "sc_update")
 
     def profileEnable(self, on: bool = True):
         self._chk(self.f.profile_enable(self.h, int(on)), "profile_enable")
 
     def profileRead(self) -> dict:
         """{kind: (device ms, launches)} accumulated since profileEnable()."""
-        ms = (C.c_double * 5)()
-        n = (C.c_int64 * 5)()
+        ms = (C.c_double * len(self.KERNEL_KINDS))()
+        n = (C.c_int64 * len(self.KERNEL_KINDS))()
         self._chk(self.f.profile_read(self.h, ms, n), "profile_read")
         return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNEL_KINDS)}
 
