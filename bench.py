@@ -214,6 +214,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--stream", default="noisy", help="input stream kind for prediction inputs: noisy|coherent|iid")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: CSDR slab exchange by the library's peer-memory kernel (default) or NCCL all-gather")
     ap.add_argument("--size", type=int, default=None, help="c4 only: grid edge (default 512); smaller sizes are for profiling runs")
     args = ap.parse_args()
 
@@ -258,9 +260,11 @@ def main():
     if args.gpus != world:
         raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run")
 
-    opt = og.CreateOptions(device=local_rank, deviceInit=cfg["device_init"], replayRng=False, shardRank=rank, shardWorld=world)
+    peer = world > 1 and args.exchange == "peer"
+    opt = og.CreateOptions(device=local_rank, deviceInit=cfg["device_init"], replayRng=False, shardRank=rank, shardWorld=world,
+                           peerExchange=peer)
     ext = {}
-    if world > 1:
+    if world > 1 and not peer:
         cache = {}
 
         def all_gather(buf, count, stream_ptr):
@@ -274,6 +278,11 @@ def main():
         opt.allGather = all_gather
     h = og.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=cfg["seed"], options=opt)
     ext["s"] = torch.cuda.ExternalStream(h.stream(), device=local_rank)
+    if peer:  # one CUDA IPC handle per rank, gathered over the process group; after this the step path never calls NCCL
+        handles = [None] * world
+        dist.all_gather_object(handles, h.peerExport())
+        h.peerAttach(handles)
+        dist.barrier()
     h.synchronize()
 
     # inputs: every prediction/none input gets the chosen stream; generated once, resident in HBM before timing
@@ -299,6 +308,8 @@ def main():
     for l in range(len(cfg["layerDescs"])):
         h.takeSCUpdateCount(l)
     h.profileEnable(True)
+    if peer:
+        h.peerTakeWaitNs()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     time.sleep(0.25 if rank == 0 else 0.0)
     barrier()
@@ -314,10 +325,15 @@ def main():
     prof = h.profileRead()
     h.profileEnable(False)
     upd = [h.takeSCUpdateCount(l) for l in range(len(cfg["layerDescs"]))]
+    ranks_info = None
     if dist is not None:
         t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mine = {"step_ms": ms / K, "kernel_ms_per_step": sum(v[0] for v in prof.values()) / K,
+                "exchange_wait_us_per_step": (h.peerTakeWaitNs() / 1e3 / K) if peer else None}
         ms = float(t.item())
+        ranks_info = [None] * world
+        dist.all_gather_object(ranks_info, mine)
     value = K / (ms / 1000.0)
 
     # ------------------------------------------------------------------------------------------------ e2e (host API)
@@ -389,7 +405,9 @@ def main():
         except Exception as e:  # the baseline must never take the GPU result down with it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
 
-    config.update({"parallelism": f"x-slab sharding over {world} GPU(s)" if world > 1 else "single GPU",
+    config.update({"parallelism": (f"x-slab sharding over {world} GPUs, CSDR slabs exchanged by "
+                                   f"{'a peer-memory (NVLink) all-gather kernel' if peer else 'NCCL all-gather'}")
+                   if world > 1 else "single GPU",
                    "l2": "per-step weight traffic (GBs) far exceeds the 126 MB L2; no flush needed" if args.workload == "c4"
                    else "weights exceed L2" if args.workload == "c2" else "L2-resident (latency-bound config)",
                    "init": "device counter-hash" if cfg["device_init"] else "std::mt19937 in reference order"})
@@ -398,7 +416,7 @@ def main():
            "config": config, "roofline": roofline, "cpu_baseline": cpu,
            "e2e": {"value": Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
            "gpu_launches": int(sum(n for _, n in prof.values())), "clocks": clk,
-           "column_steps_per_s": value * sum(ld.hiddenSize[0] * ld.hiddenSize[1] * c for ld, c in zip(cfg["layerDescs"], counts)) / K}
+           "ranks": ranks_info, "column_steps_per_s": value * sum(ld.hiddenSize[0] * ld.hiddenSize[1] * c for ld, c in zip(cfg["layerDescs"], counts)) / K}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -52,10 +52,17 @@ public:
     int shardRank, shardWorld;
     AllGatherFn allGather;
     void *allGatherUser;
+    // Alternative to the callback for one process per GPU on one NVLink node: set peerExchange before the first layer is
+    // created, exchange the 64-byte handles of peerExport() between the ranks (any transport) and hand all of them to
+    // peerAttach(). The all-gathers then run as one peer-memory kernel each on this system's stream (no NCCL, no host).
+    bool peerExchange;
+    void peerExport(void *handle64);
+    void peerAttach(const void *handles64, int world);
 
     ComputeSystem()
         : batchSize1(512), batchSize2(2, 2), batchSize3(2, 2, 2), replayRng(false), device(-1), deviceInit(false),
-          deviceInitSeed(0), deviceInitMatrix(0), shardRank(0), shardWorld(1), allGather(nullptr), allGatherUser(nullptr) {}
+          deviceInitSeed(0), deviceInitMatrix(0), shardRank(0), shardWorld(1), allGather(nullptr), allGatherUser(nullptr),
+          peerExchange(false) {}
 
     static void setNumThreads(int numThreads);
     static int getNumThreads();

@@ -31,10 +31,29 @@ typedef struct ogn_create_options {
     void *all_gather_user;
     int ensemble;          /* number of independent lock-stepped hierarchies (>= 1) */
     const uint32_t *ensemble_seeds; /* optional [ensemble]; default seed + k */
+    int peer_exchange;     /* 1 (with shard_world > 1, one process per GPU on one NVLink node): exchange the CSDR slabs with
+                              the library's own peer-memory kernel instead of the all_gather callback; call ogn_peer_export,
+                              pass every rank's handle to ogn_peer_attach, then step */
 } ogn_create_options;
 
 /* ogn_create with options. ogn_create(desc, seed, out) == ogn_create_ex with {device -1, device_init 0, replay_rng 1}. */
 int ogn_create_ex(const ogn_hierarchy_desc *desc, uint32_t seed, const ogn_create_options *opt, void **out);
+
+/* Peer-memory exchange set-up (peer_exchange = 1). export: the 64-byte CUDA IPC handle of this rank's exchange arena.
+ * attach: handles = world x 64 bytes in rank order (this rank's own entry is ignored); maps the peers' arenas. The
+ * transport of the handles between the processes is the caller's (torch.distributed, MPI, a file ...). */
+#define OGN_PEER_HANDLE_BYTES 64
+int ogn_peer_export(void *h, void *handle_out);
+int ogn_peer_attach(void *h, const void *handles, int world);
+/* Nanoseconds of device time this rank's exchange kernels spent waiting for the other ranks since the last call (load
+ * imbalance + NVLink latency; synchronises). */
+uint64_t ogn_peer_take_wait_ns(void *h);
+
+/* The x-slab plan of one (hidden grid, visible grid, radius) pairing for `rank` of `world` (host only, no device
+ * needed): out[0..1] = hidden rows [x0,x1) this rank owns (forward, Predictor, F copy); out[2..3] = visible rows
+ * [vx0,vx1) whose reconstruction / learn it runs; out[4..5] = hidden rows [rx0,rx1) whose R copy it keeps (owner +
+ * replicas). Returns non-zero if hidden_x is not a multiple of world. */
+int ogn_shard_plan(int hidden_x, int visible_x, int radius, int rank, int world, int out[6]);
 
 /* Hierarchy::step on inputs that already live in device memory (int32 [member][columns] per input). Fully asynchronous
  * on the hierarchy's stream: nothing is copied to or from the host. */
@@ -48,11 +67,12 @@ int ogn_ensemble_size(void *h);
 /* (hidden column, visible column) pairs whose weights SparseCoder l rewrote since the last call: the data-dependent
  * term U of the algorithmic byte count. Synchronises. */
 uint64_t ogn_take_sc_update_count(void *h, int l);
-/* Launch accounting. Kernel kinds, in array order: 0 SparseCoder forward (K2), 1 SparseCoder learn (K3), 2 Predictor
- * learn+activate (K6+K7+K8), 3 Actor forward (K9), 4 Actor learn (K11). enable(on) resets the counters; with on != 0
+/* Launch accounting. Kernel kinds, in array order: 0 SparseCoder forward (K2), 1 SparseCoder learn (K3: the
+ * reconstruction when learn runs as two kernels, else the fused learn), 2 Predictor learn+activate (K6+K7+K8), 3 Actor
+ * forward (K9), 4 Actor learn (K11), 5 SparseCoder learn part 2 (work-list update). enable(on) resets the counters; with on != 0
  * every launch is bracketed by CUDA events on the hierarchy's stream. read() synchronises and returns the accumulated
  * device milliseconds and launch counts per kind (arrays of OGN_KERNEL_KINDS). */
-#define OGN_KERNEL_KINDS 5
+#define OGN_KERNEL_KINDS 6
 int ogn_profile_enable(void *h, int on);
 int ogn_profile_read(void *h, double *ms, int64_t *launches);
 int ogn_device_count(void);

@@ -166,6 +166,20 @@ int ogn_actor_learn(const ogn_actor_args *args_host, int Hx, int Hy, int Hz, con
                     const float *hidden_values_prev, const float *hidden_values, float q, float g, float alpha, float beta,
                     int mimic, float *hidden_activations, void *stream);
 
+/* Peer-memory all-gather of a sharded CSDR (multi-GPU, one process per GPU): base[r] is rank r's exchange arena as mapped
+ * in THIS process (CUDA IPC); the buffer lives at the same offset in every arena. One launch: this rank's slab
+ * [rank*count, (rank+1)*count) is stored into every peer's arena with 128-bit NVLink stores, the last block to finish
+ * raises this rank's arrival flag (arena word `rank`, value epoch) in every peer with a system-scope release store and
+ * waits until every peer's flag in the local arena reached epoch (acquire loads, bounded by timeout_ns; on timeout
+ * *err_flag, a host-mapped word, is set to 1). Kernels queued behind it on the stream see the complete buffer. */
+#define OGN_MAX_PEERS 16
+typedef struct ogn_peer_table {
+    int *base[OGN_MAX_PEERS];
+    int rank, world;
+} ogn_peer_table;
+int ogn_peer_allgather(const ogn_peer_table *table_host, int64_t offset_ints, int count_per_rank, unsigned epoch,
+                       unsigned long long timeout_ns, unsigned *err_flag, void *stream);
+
 /* Weight (re)layout between the reference's CSR value order and the device layouts, for hidden columns
  * [col0, col1) (col = oy + ox*Hy) of one ensemble member. csr is a DEVICE staging buffer holding CSR-order values;
  * csr[0] is the value with global CSR index csr_base (normally the CSR block offset of column col0). which: 0 = F,

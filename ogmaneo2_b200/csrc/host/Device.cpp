@@ -32,7 +32,88 @@ DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
     cudaCheck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
 }
 
+// ---- peer arena --------------------------------------------------------------------------------------------------
+void DeviceContext::arenaCreate(size_t bytes, int rank, int world) {
+    if (world > OGN_MAX_PEERS) throw std::runtime_error("ogmaneo-b200: at most 16 devices can share a peer exchange");
+    arena.reset(new PeerArena());
+    arena->capInts = std::max<size_t>(bytes / sizeof(int), PeerArena::kHeaderInts * 2);
+    arena->rank = rank; arena->world = world;
+    cudaCheck(cudaMalloc((void **)&arena->base, arena->capInts * sizeof(int)), "cudaMalloc(peer arena)");
+    cudaCheck(cudaMemset(arena->base, 0, arena->capInts * sizeof(int)), "cudaMemset(peer arena)");
+    cudaCheck(cudaHostAlloc((void **)&arena->errHost, sizeof(unsigned), cudaHostAllocMapped), "cudaHostAlloc");
+    *arena->errHost = 0;
+    cudaCheck(cudaHostGetDevicePointer((void **)&arena->errDev, arena->errHost, 0), "cudaHostGetDevicePointer");
+    arena->peer[rank] = arena->base;
+}
+
+int *DeviceContext::arenaAlloc(size_t nInts) {
+    PeerArena &a = *arena;
+    const size_t start = (a.usedInts + 63) & ~(size_t)63; // 256-byte aligned: slabs stay 16-byte aligned for 128-bit stores
+    if (start + nInts > a.capInts)
+        throw std::runtime_error("ogmaneo-b200: peer exchange arena exhausted (raise OGN_PEER_ARENA_MB)");
+    a.usedInts = start + nInts;
+    return a.base + start;
+}
+
+void DeviceContext::arenaExport(void *handle64) const {
+    if (!arena) throw std::runtime_error("ogmaneo-b200: no peer arena (create with peer_exchange and shard_world > 1)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    cudaCheck(cudaIpcGetMemHandle(&h, arena->base), "cudaIpcGetMemHandle");
+    std::memcpy(handle64, &h, sizeof(h));
+}
+
+void DeviceContext::arenaAttach(const void *handles64, int world) {
+    if (!arena) throw std::runtime_error("ogmaneo-b200: no peer arena (create with peer_exchange and shard_world > 1)");
+    if (world != arena->world) throw std::invalid_argument("ogmaneo-b200: peer attach: world size mismatch");
+    cudaCheck(cudaSetDevice(device), "cudaSetDevice");
+    for (int r = 0; r < world; r++) {
+        if (r == arena->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char *)handles64 + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        cudaCheck(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+        arena->peer[r] = (int *)p;
+    }
+    arena->attached = true;
+}
+
+void DeviceContext::peerAllGather(int *buffer, int countPerRank) {
+    PeerArena &a = *arena;
+    if (!a.attached) throw std::runtime_error("ogmaneo-b200: peer exchange used before ogn_peer_attach");
+    if (!inArena(buffer)) throw std::runtime_error("ogmaneo-b200: peer all-gather of a buffer outside the exchange arena");
+    ogn_peer_table t;
+    std::memset(&t, 0, sizeof(t));
+    for (int r = 0; r < a.world; r++) t.base[r] = a.peer[r];
+    t.rank = a.rank; t.world = a.world;
+    static const unsigned long long timeoutNs = [] {
+        const char *e = std::getenv("OGN_PEER_TIMEOUT_MS");
+        return (unsigned long long)(e ? std::atoll(e) : 5000) * 1000000ull;
+    }();
+    kernelCheck(ogn_peer_allgather(&t, buffer - a.base, countPerRank, ++a.epoch, timeoutNs, a.errDev, stream), "peer_allgather");
+}
+
+unsigned long long DeviceContext::peerTakeWaitNs() {
+    if (!arena) return 0;
+    unsigned long long v = 0;
+    cudaCheck(cudaMemcpyAsync(&v, arena->base + 18, sizeof(v), cudaMemcpyDeviceToHost, stream), "D2H");
+    cudaCheck(cudaMemsetAsync(arena->base + 18, 0, sizeof(v), stream), "memset");
+    sync();
+    return v;
+}
+
+void DeviceContext::peerCheck() const {
+    if (arena && arena->errHost && *(volatile unsigned *)arena->errHost)
+        throw std::runtime_error("ogmaneo-b200: a peer all-gather timed out waiting for another rank");
+}
+
 DeviceContext::~DeviceContext() {
+    if (arena) {
+        for (int r = 0; r < arena->world; r++)
+            if (r != arena->rank && arena->peer[r]) cudaIpcCloseMemHandle(arena->peer[r]);
+        if (arena->base) cudaFree(arena->base);
+        if (arena->errHost) cudaFreeHost(arena->errHost);
+    }
     for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : eventPool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -47,6 +128,7 @@ cudaEvent_t DeviceContext::takeEvent() {
 
 void DeviceContext::profileCollect() {
     sync();
+    peerCheck();
     for (auto &r : recs) {
         float ms = 0.0f;
         cudaCheck(cudaEventElapsedTime(&ms, r.a, r.b), "cudaEventElapsedTime");
@@ -321,11 +403,18 @@ void ComputeSystem::setNumThreads(int numThreads) { g_numThreads = numThreads; }
 int ComputeSystem::getNumThreads() { return g_numThreads; }
 
 detail::DeviceContext &ComputeSystem::context() {
-    if (!ctx) ctx = std::make_shared<detail::DeviceContext>(device);
-    else detail::cudaCheck(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (!ctx) {
+        ctx = std::make_shared<detail::DeviceContext>(device);
+        if (peerExchange && shardWorld > 1) {
+            const char *e = std::getenv("OGN_PEER_ARENA_MB");
+            ctx->arenaCreate((size_t)(e ? std::atoll(e) : 64) << 20, shardRank, shardWorld);
+        }
+    } else detail::cudaCheck(cudaSetDevice(ctx->device), "cudaSetDevice");
     return *ctx;
 }
-void ComputeSystem::synchronize() { context().sync(); }
+void ComputeSystem::synchronize() { context().sync(); context().peerCheck(); }
+void ComputeSystem::peerExport(void *handle64) { context().arenaExport(handle64); }
+void ComputeSystem::peerAttach(const void *handles64, int world) { context().arenaAttach(handles64, world); }
 void *ComputeSystem::stream() { return (void *)context().stream; }
 
 } // namespace ogmaneo

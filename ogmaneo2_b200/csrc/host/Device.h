@@ -24,12 +24,37 @@ inline void kernelCheck(int code, const char *what) { cudaCheck((cudaError_t)cod
 
 enum KernelKind { kScForward = 0, kScLearn = 1, kPredStep = 2, kActorForward = 3, kActorLearn = 4, kScUpdate = 5, kKernelKinds = 6 };
 
+// Peer-memory exchange of sharded CSDRs (one process per GPU on one NVLink / NVSwitch node). Every CSDR buffer a
+// sharded layer exchanges is carved out of ONE arena per device, in construction order, so it sits at the same offset on
+// every rank; the arena is exported with CUDA IPC and each rank maps its peers' arenas. An all-gather is then one kernel
+// (ogn_peer_allgather): every rank stores its slab straight into the other ranks' arenas over NVLink, raises a flag in
+// each of them and waits for theirs. No NCCL call, no host round trip.
+struct PeerArena {
+    static constexpr size_t kHeaderInts = 64; // [0..15] arrival flags, [16] blocks done, [18..19] ns waited for peers (total), [20..21] scratch
+    int *base = nullptr;
+    size_t capInts = 0, usedInts = kHeaderInts;
+    int rank = 0, world = 1;
+    int *peer[OGN_MAX_PEERS] = {};
+    bool attached = false;
+    unsigned epoch = 0;
+    unsigned *errHost = nullptr, *errDev = nullptr; // mapped pinned word: set by a kernel whose wait timed out
+};
+
 // One device + one stream. Created lazily by ComputeSystem::context(); throws if no sm_100 device is usable.
 struct DeviceContext {
     int device;
     cudaStream_t stream;
     explicit DeviceContext(int device);
     ~DeviceContext();
+    std::unique_ptr<PeerArena> arena;
+    void arenaCreate(size_t bytes, int rank, int world);
+    int *arenaAlloc(size_t nInts);                       // zero-initialised, 256-byte aligned
+    bool inArena(const int *p) const { return arena && p >= arena->base && p < arena->base + arena->capInts; }
+    void arenaExport(void *handle64) const;
+    void arenaAttach(const void *handles64, int world);
+    void peerAllGather(int *buffer, int countPerRank);   // in-place all-gather of [world][countPerRank] ints, on `stream`
+    void peerCheck() const;                              // throws if a peer wait timed out
+    unsigned long long peerTakeWaitNs();                 // device time spent waiting for other ranks since the last call (syncs)
     void sync() const { cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize"); }
 
     // Launch accounting: counts are always kept; with profiling on, every launch is bracketed by two CUDA events on
@@ -69,9 +94,9 @@ public:
     ~DevBuf() { release(); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    DevBuf(DevBuf &&o) noexcept : p_(o.p_), n_(o.n_), owned_(o.owned_) { o.p_ = nullptr; o.n_ = 0; o.owned_ = true; }
     DevBuf &operator=(DevBuf &&o) noexcept {
-        if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+        if (this != &o) { release(); p_ = o.p_; n_ = o.n_; owned_ = o.owned_; o.p_ = nullptr; o.n_ = 0; o.owned_ = true; }
         return *this;
     }
     void alloc(size_t n) {
@@ -79,13 +104,14 @@ public:
         n_ = n;
         if (n) cudaCheck(cudaMalloc((void **)&p_, n * sizeof(T)), "cudaMalloc");
     }
+    void borrow(T *p, size_t n) { release(); p_ = p; n_ = n; owned_ = false; } // memory owned by someone else (peer arena)
     void allocZero(size_t n, cudaStream_t s) {
         alloc(n);
         if (n) cudaCheck(cudaMemsetAsync(p_, 0, n * sizeof(T), s), "cudaMemsetAsync");
     }
     void release() {
-        if (p_) cudaFree(p_);
-        p_ = nullptr; n_ = 0;
+        if (p_ && owned_) cudaFree(p_);
+        p_ = nullptr; n_ = 0; owned_ = true;
     }
     void cloneFrom(const DevBuf &o, cudaStream_t s) {
         alloc(o.n_);
@@ -103,6 +129,7 @@ public:
 private:
     T *p_ = nullptr;
     size_t n_ = 0;
+    bool owned_ = true;
 };
 
 template <typename T> class PinnedBuf {

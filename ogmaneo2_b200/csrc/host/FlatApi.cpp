@@ -1,5 +1,6 @@
 // csrc/host/FlatApi.cpp — the flat C ABI (include/ogn_hierarchy_api.h, prefix ogn_) on top of the C++ drop-in classes,
 // plus product-only entry points (include/ogn_b200.h): device-resident stepping, ensembles, sharding, hash init.
+#include <algorithm>
 #include <ogmaneo/Hierarchy.h>
 
 #include <cstring>
@@ -75,6 +76,7 @@ int ogn_create_ex(const ogn_hierarchy_desc *d, uint32_t seed, const ogn_create_o
             if (opt->replay_rng) H->cs.replayRng = true;
             H->cs.shardRank = opt->shard_rank; H->cs.shardWorld = opt->shard_world > 0 ? opt->shard_world : 1;
             H->cs.allGather = opt->all_gather; H->cs.allGatherUser = opt->all_gather_user;
+            H->cs.peerExchange = opt->peer_exchange != 0;
             ensemble = opt->ensemble > 0 ? opt->ensemble : 1;
         }
         if (ensemble > 1 || (opt && opt->ensemble_seeds)) {
@@ -258,6 +260,37 @@ int ogn_load(const char *path, uint32_t seed, void **out) {
 uint32_t ogn_rng_peek(void *h) {
     std::mt19937 c = ((Handle *)h)->cs.rng;
     return (uint32_t)c();
+}
+int ogn_shard_plan(int Hx, int Vx, int r, int rank, int world, int out[6]) {
+    return guard([&] {
+        int a = 0, b = 0;
+        detail::slabOf(Hx, rank, world, a, b);
+        // project(): (int)(pos * (float)in / (float)out + 0.5f), field [c - r, c + r] clamped (Helpers.cpp:245-262)
+        const float scale = (float)Vx / (float)Hx;
+        auto lo = [&](int o) { return std::max(0, (int)(o * scale + 0.5f) - r); };
+        auto hi = [&](int o) { return std::min(Vx - 1, (int)(o * scale + 0.5f) + r); };
+        int vx0 = Vx, vx1 = 0;
+        for (int o = a; o < b; o++)
+            if (hi(o) >= lo(o)) { vx0 = std::min(vx0, lo(o)); vx1 = std::max(vx1, hi(o) + 1); }
+        if (vx1 < vx0) vx0 = vx1 = 0;
+        int rx0 = Hx, rx1 = 0;
+        for (int o = 0; o < Hx; o++)
+            if (hi(o) >= lo(o) && lo(o) < vx1 && hi(o) >= vx0) { rx0 = std::min(rx0, o); rx1 = std::max(rx1, o + 1); }
+        if (rx1 < rx0) rx0 = rx1 = 0;
+        if (world <= 1) { vx0 = 0; vx1 = Vx; rx0 = 0; rx1 = Hx; }
+        out[0] = a; out[1] = b; out[2] = vx0; out[3] = vx1; out[4] = rx0; out[5] = rx1;
+    });
+}
+int ogn_peer_export(void *hh, void *handle_out) {
+    return guard([&] { ((Handle *)hh)->cs.peerExport(handle_out); });
+}
+int ogn_peer_attach(void *hh, const void *handles, int world) {
+    return guard([&] { ((Handle *)hh)->cs.peerAttach(handles, world); });
+}
+uint64_t ogn_peer_take_wait_ns(void *hh) {
+    uint64_t v = 0;
+    guard([&] { v = ((Handle *)hh)->cs.context().peerTakeWaitNs(); });
+    return v;
 }
 int ogn_profile_enable(void *hh, int on) {
     return guard([&] {

@@ -42,7 +42,8 @@ void Predictor::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, const std:
         ws.sets[v].allocate(*ctx, Geometry::get(hidden, vlds[v].size, vlds[v].radius), batch, false, false, x0, x1);
     const size_t ncols = (size_t)hidden.x * hidden.y * batch;
     acts.allocZero(ncols * hidden.z, ctx->stream);
-    hiddenCs.allocZero(ncols, ctx->stream);
+    if (ctx->arena) hiddenCs.borrow(ctx->arenaAlloc(ncols), ncols); // exchanged CSDR: see SparseCoder::Impl::allocate
+    else hiddenCs.allocZero(ncols, ctx->stream);
     for (int p = 0; p < 2; p++) {
         prev_[p].clear(); prev_[p].resize(vlds.size());
         for (size_t v = 0; v < vlds.size(); v++) prev_[p][v].allocZero((size_t)vlds[v].size.x * vlds[v].size.y * batch, ctx->stream);
@@ -99,8 +100,9 @@ void Predictor::stepDevice(ComputeSystem &cs, bool learn, const int *targetDev, 
         m.prevCur = 1 - m.prevCur;
         m.csDirty = m.actDirty = m.prevDirty = true;
         if (m.world > 1) {
-            if (!cs.allGather) throw std::runtime_error("ogmaneo-b200: shardWorld > 1 needs ComputeSystem::allGather");
-            cs.allGather(cs.allGatherUser, m.hiddenCs.ptr(), (m.x1 - m.x0) * hiddenSize.y, (void *)ctx.stream);
+            if (ctx.arena && ctx.inArena(m.hiddenCs.ptr())) ctx.peerAllGather(m.hiddenCs.ptr(), (m.x1 - m.x0) * hiddenSize.y);
+            else if (cs.allGather) cs.allGather(cs.allGatherUser, m.hiddenCs.ptr(), (m.x1 - m.x0) * hiddenSize.y, (void *)ctx.stream);
+            else throw std::runtime_error("ogmaneo-b200: shardWorld > 1 needs ComputeSystem::allGather or peerExchange");
         }
     }
 }

@@ -41,7 +41,11 @@ void SparseCoder::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, const st
     for (size_t v = 0; v < vlds.size(); v++)
         ws.sets[v].allocate(*ctx, Geometry::get(hidden, vlds[v].size, vlds[v].radius), batch, true, true, x0, x1);
     const size_t ncols = (size_t)hidden.x * hidden.y * batch;
-    cs_[0].allocZero(ncols, ctx->stream); cs_[1].allocZero(ncols, ctx->stream);
+    if (ctx->arena) { // sharded with peer exchange: the CSDRs live in the exchange arena (same offset on every rank)
+        cs_[0].borrow(ctx->arenaAlloc(ncols), ncols); cs_[1].borrow(ctx->arenaAlloc(ncols), ncols);
+    } else {
+        cs_[0].allocZero(ncols, ctx->stream); cs_[1].allocZero(ncols, ctx->stream);
+    }
     upd.allocZero(1, ctx->stream);
     {   // one learn launch covers a run of equally-shaped visible layers: size the list for the largest run
         size_t need = 0, v = 0;
@@ -102,8 +106,9 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
     kernelCheck(ogn_sc_forward(&fa, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, out, sharded ? nullptr : copyOut,
                                ctx.stream), "sc_forward"); }
     if (sharded) {
-        if (!cs.allGather) throw std::runtime_error("ogmaneo-b200: shardWorld > 1 needs ComputeSystem::allGather");
-        cs.allGather(cs.allGatherUser, out, (m.x1 - m.x0) * hiddenSize.y, (void *)ctx.stream);
+        if (ctx.arena && ctx.inArena(out)) ctx.peerAllGather(out, (m.x1 - m.x0) * hiddenSize.y);
+        else if (cs.allGather) cs.allGather(cs.allGatherUser, out, (m.x1 - m.x0) * hiddenSize.y, (void *)ctx.stream);
+        else throw std::runtime_error("ogmaneo-b200: shardWorld > 1 needs ComputeSystem::allGather or peerExchange");
         if (copyOut)
             cudaCheck(cudaMemcpyAsync(copyOut, out, (size_t)hiddenSize.x * hiddenSize.y * sizeof(int), cudaMemcpyDeviceToDevice,
                                       ctx.stream), "hiddenCs D2D");

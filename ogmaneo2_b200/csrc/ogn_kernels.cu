@@ -699,6 +699,66 @@ __global__ void k_test_tanhf(const float *in, float *out, long long n) {
     if (i < n) out[i] = ogn_tanhf(in[i]);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer-memory all-gather of a sharded CSDR (see ogn_peer_allgather in ogn_kernels_api.h). blockIdx.y = peer.
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+k_peer_allgather(const __grid_constant__ ogn_peer_table T, long long off, int count, unsigned epoch, unsigned long long timeoutNs,
+                 unsigned *errFlag) {
+    __shared__ int lastBlock;
+    if (T.world > 1 && count > 0) {
+        int p = blockIdx.y;
+        if (p >= T.rank) ++p;
+        const int *src = T.base[T.rank] + off + (long long)T.rank * count;
+        int *dst = T.base[p] + off + (long long)T.rank * count;
+        const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+        if ((((unsigned long long)src | (unsigned long long)dst) & 15ull) == 0) {
+            const int n4 = count >> 2;
+            for (int i = tid; i < n4; i += nth) reinterpret_cast<int4 *>(dst)[i] = __ldg(reinterpret_cast<const int4 *>(src) + i);
+            for (int i = (n4 << 2) + tid; i < count; i += nth) dst[i] = __ldg(src + i);
+        } else
+            for (int i = tid; i < count; i += nth) dst[i] = __ldg(src + i);
+    }
+    __threadfence_system(); // this thread's peer stores are ordered before the arrival flag below
+    __syncthreads();
+    unsigned *hdr = reinterpret_cast<unsigned *>(T.base[T.rank]);
+    if (threadIdx.x == 0) lastBlock = atomicAdd(&hdr[16], 1u) == gridDim.x * gridDim.y - 1u;
+    __syncthreads();
+    if (!lastBlock) return;
+    if (threadIdx.x == 0) hdr[16] = 0;
+    const int q = threadIdx.x;
+    if (q < T.world && q != T.rank) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned *>(T.base[q]) + T.rank, epoch); // "rank has delivered exchange #epoch" in q's arena
+        const unsigned long long t0 = global_ns();
+        unsigned long long t1 = t0;
+        while ((int)(ld_acquire_sys(hdr + q) - epoch) < 0) {
+            t1 = global_ns();
+            if (t1 - t0 > timeoutNs) { *errFlag = 1u; break; }
+        }
+        // diagnostics: the longest wait of this exchange goes to words 18/19 (ns waited for peers, 64-bit total)
+        atomicMax(reinterpret_cast<unsigned long long *>(hdr + 20), t1 - t0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long *acc = reinterpret_cast<unsigned long long *>(hdr + 18), *mx = reinterpret_cast<unsigned long long *>(hdr + 20);
+        *acc += *mx;
+        *mx = 0;
+    }
+}
+
 inline int group_lanes(int z) {
     int g = 1;
     while (g < z && g < 32) g <<= 1;
@@ -888,6 +948,18 @@ int ogn_actor_learn(const ogn_actor_args *args, int Hx, int Hy, int Hz, const in
     OGN_DISPATCH_G(g, (k_actor_learn<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, npacks, ppr, target_cs_prev,
                                                                                   hidden_values_prev, hidden_values, q, g_, alpha, beta,
                                                                                   mimic, hidden_activations)));
+    return launch_status();
+}
+
+int ogn_peer_allgather(const ogn_peer_table *table, int64_t offset_ints, int count_per_rank, unsigned epoch,
+                       unsigned long long timeout_ns, unsigned *err_flag, void *stream) {
+    if (table->world <= 1) return 0;
+    if (table->world > OGN_MAX_PEERS || table->rank < 0 || table->rank >= table->world) return (int)cudaErrorInvalidValue;
+    int bx = (count_per_rank / 4 + 1023) / 1024; // ~4 x 16-byte stores per thread
+    if (bx < 1) bx = 1;
+    if (bx > 16) bx = 16;
+    dim3 grid((unsigned)bx, (unsigned)(table->world - 1));
+    k_peer_allgather<<<grid, 256, 0, (cudaStream_t)stream>>>(*table, offset_ints, count_per_rank, epoch, timeout_ns, err_flag);
     return launch_status();
 }
 

@@ -21,7 +21,7 @@ ALL_GATHER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
 class _COptions(C.Structure):
     _fields_ = [("device", C.c_int), ("device_init", C.c_int), ("replay_rng", C.c_int), ("shard_rank", C.c_int),
                 ("shard_world", C.c_int), ("all_gather", ALL_GATHER_FN), ("all_gather_user", C.c_void_p),
-                ("ensemble", C.c_int), ("ensemble_seeds", C.POINTER(C.c_uint32))]
+                ("ensemble", C.c_int), ("ensemble_seeds", C.POINTER(C.c_uint32)), ("peer_exchange", C.c_int)]
 
 
 @dataclasses.dataclass
@@ -34,6 +34,7 @@ class CreateOptions:
     allGather: Optional[Callable] = None  # f(buffer_ptr: int, count_per_rank: int, stream_ptr: int)
     ensemble: int = 1
     ensembleSeeds: Optional[Sequence[int]] = None
+    peerExchange: bool = False    # shardWorld > 1, one process per GPU: the library's own peer-memory all-gather kernel
 
 
 _PRODUCT_SIGS = {
@@ -45,6 +46,10 @@ _PRODUCT_SIGS = {
     "ensemble_size": (C.c_int, [_VP]),
     "take_sc_update_count": (C.c_uint64, [_VP, C.c_int]),
     "device_count": (C.c_int, []),
+    "shard_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "peer_export": (C.c_int, [_VP, C.c_void_p]),
+    "peer_attach": (C.c_int, [_VP, C.c_void_p, C.c_int]),
+    "peer_take_wait_ns": (C.c_uint64, [_VP]),
     "profile_enable": (C.c_int, [_VP, C.c_int]),
     "profile_read": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
@@ -79,6 +84,7 @@ class Hierarchy(FlatHierarchy):
         co = _COptions()
         co.device, co.device_init, co.replay_rng = opt.device, int(opt.deviceInit), int(opt.replayRng)
         co.shard_rank, co.shard_world, co.ensemble = opt.shardRank, opt.shardWorld, opt.ensemble
+        co.peer_exchange = int(opt.peerExchange)
         self._cb = None
         if opt.allGather is not None:
             user_fn = opt.allGather
@@ -113,6 +119,22 @@ class Hierarchy(FlatHierarchy):
         """inputPtrs: device addresses (ints) of int32 [member][columns] buffers. Asynchronous."""
         ptrs = (C.c_void_p * len(inputPtrs))(*[C.c_void_p(int(p)) for p in inputPtrs])
         self._chk(self.f.step_device(self.h, ptrs, int(learnEnabled), float(reward), int(mimic)), "step_device")
+
+    def peerExport(self) -> bytes:
+        """The 64-byte CUDA IPC handle of this rank's exchange arena (CreateOptions.peerExchange)."""
+        buf = C.create_string_buffer(64)
+        self._chk(self.f.peer_export(self.h, buf), "peer_export")
+        return buf.raw
+
+    def peerAttach(self, handles: Sequence[bytes]):
+        """handles: every rank's peerExport() in rank order (gathered by the caller, e.g. all_gather_object)."""
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != 64 * len(handles):
+            raise ValueError("peer handles must be 64 bytes each")
+        self._chk(self.f.peer_attach(self.h, C.c_char_p(blob), len(handles)), "peer_attach")
+
+    def peerTakeWaitNs(self) -> int:
+        return int(self.f.peer_take_wait_ns(self.h))
 
     def predictionCsDevice(self, i: int) -> int:
         return int(self.f.prediction_cs_device(self.h, i) or 0)

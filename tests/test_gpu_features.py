@@ -198,6 +198,23 @@ def test_sharded_equals_unsharded(product, world):
         assert np.array_equal(merged.view(np.int32), full.view(np.int32)), f"layer {l} SparseCoder weights differ after sharded learning"
 
 
+def test_peer_memory_exchange_multi_gpu(product):
+    """>= 2 GPUs: one process per GPU, CSDR slabs exchanged by the library's peer-memory kernel (no NCCL); see
+    tests/dist_peer_worker.py. Skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    n = product.cdll().ogn_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 4 if n >= 4 else 2
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29655", os.path.join(root, "tests", "dist_peer_worker.py")]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count(" ok") == world
+
+
 def test_get_set_state_and_copy_semantics(product):
     """Hierarchy::getState/setState round trip through the flat ABI's save/load + continued stepping determinism."""
     cfg = configs.c2_video(8, 3)
