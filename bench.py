@@ -36,6 +36,9 @@ from ogmaneo2_b200 import configs, streams  # noqa: E402
 from ogmaneo2_b200.flat_api import FlatHierarchy, InputType  # noqa: E402
 
 METRIC = "hierarchy_steps_per_s_learn_on"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel at the default workload (C4 512x512), from the
+# `ncu --set full` capture summarised in profiles/README.md (filled in from the capture; None = not captured)
+TRAFFIC = {}
 UNIT = "steps/s"
 
 
@@ -242,8 +245,9 @@ def main():
         return
 
     # ------------------------------------------------------------------------------------------------ B200 arm
-    K = args.steps if args.steps is not None else (200 if args.workload == "c4" else 2000)
-    W = args.warmup if args.warmup is not None else (20 if args.workload == "c4" else 200)
+    # defaults: the step counts SURVEY.md §8d prescribes for each config (C4: 200 warm-up + 300 timed)
+    K = args.steps if args.steps is not None else (300 if args.workload == "c4" else 2000)
+    W = args.warmup if args.warmup is not None else (200 if args.workload == "c4" else 300)
     W = max(W, 3)
     import torch
     import ogmaneo2_b200 as og
@@ -307,7 +311,7 @@ def main():
     barrier()
     for l in range(len(cfg["layerDescs"])):
         h.takeSCUpdateCount(l)
-    h.profileEnable(True)
+    h.profileEnable(os.environ.get("OGN_BENCH_NOPROF") != "1")
     if peer:
         h.peerTakeWaitNs()
     clocks = ClockSampler(local_rank) if rank == 0 else None
@@ -388,10 +392,11 @@ def main():
         kernels[kind] = {"launches": int(n), "ms_per_launch": kms / n, "alg_bytes_per_launch": ab / n if ab else None,
                          "achieved_gbs": (ab / n) / (kms / n * 1e-3) / 1e9 if ab and kms > 0 else None,
                          "share_of_step": kms / ms}
-    dom = max((k for k in kernels if kernels[k]["achieved_gbs"]), key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches"])
+    cand = [k for k in kernels if kernels[k]["achieved_gbs"]]
+    dom = max(cand, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches"]) if cand else None
     total_alg = sum(alg.values())
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["achieved_gbs"] / peak if dom else None, "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
                 "step_achieved_gbs": total_alg / (ms * 1e-3) / 1e9, "step_frac": total_alg / (ms * 1e-3) / 1e9 / peak,
                 "alg_bytes_per_step_per_gpu": total_alg / K, "kernels": kernels,
                 "sc_pairs_rewritten_per_step": [u / K for u in upd]}

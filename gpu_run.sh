@@ -1,11 +1,8 @@
 cd /root/repo
 mkdir -p gpurun_out
-show() { tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); r=d['roofline']
-print('N=%d steps/s %.1f ms/step %.3f e2e %.1f step_frac %.3f upd %s'%(d['n_gpus'],d['value'],d['ms_per_step'],d['e2e']['value'],r['step_frac'],r['sc_pairs_rewritten_per_step']), ' '.join('%s %.3fms %.0fGB/s'%(k,v['ms_per_launch'],v['achieved_gbs'] or 0) for k,v in r['kernels'].items()))"; }
-timeout 600 python -m pytest tests/test_gpu_features.py -m gpu -x -q -k "peer or sharded" > gpurun_out/tests_peer.log 2>&1; tail -15 gpurun_out/tests_peer.log
-N=${NGPU:-2}
-for ex in peer nccl; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 100 --warmup 100 --no-cpu --exchange $ex > gpurun_out/n${N}_$ex.log 2>&1; tail -3 gpurun_out/n${N}_$ex.log | cut -c1-300; echo $ex; cat gpurun_out/n${N}_$ex.log | show
-done
+python bench.py --size 184 --steps 100 --warmup 100 --no-cpu > gpurun_out/b184.log 2>&1; python -c "
+import json;d=json.loads(open('gpurun_out/b184.log').read().strip().split('\n')[-1]);print('with events ms/step',d['ms_per_step'], {k:v['ms_per_launch'] for k,v in d['roofline']['kernels'].items()})"
+OGN_BENCH_NOPROF=1 python bench.py --size 184 --steps 100 --warmup 100 --no-cpu 2>&1 | tail -3 | cut -c1-400
+python bench.py --size 184 --steps 30 --warmup 30 --no-cpu > gpurun_out/plain184.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,sm__cycles_elapsed.max,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -s 200 -c 40 --csv --log-file gpurun_out/launches_184.csv python bench.py --size 184 --steps 30 --warmup 30 --no-cpu > gpurun_out/ncu184.log 2>&1
+tail -2 gpurun_out/launches_184.csv | cut -c1-300

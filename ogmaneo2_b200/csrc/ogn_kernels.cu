@@ -16,6 +16,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <set>
+
 #include "../../include/ogn_kernels_api.h"
 #include "ogn_libm.h"
 
@@ -798,15 +801,21 @@ static inline bool vec_row(int z) { return z == 8 || z == 16 || z == 32; }
 static inline bool vec_geo(const ogn_rf &g) {
     return (long long)g.max_nx * g.max_nyf * g.Vz < (1ll << 20) && g.max_nyf < 0xFFF && g.max_nx > 0 && g.max_nyf > 0;
 }
-// OGN_KERNELS: "scalar" forces the generic one-cell-per-lane kernels; "vec1"/"vec2" pick the loads-in-flight depth of the
-// 128-bit kernels (8 or 16 line loads per lane before the first add). Default vec1 (measured: profiles/README.md).
+// OGN_KERNELS selects the step kernels: "scalar" = the generic one-cell-per-lane kernels (always used when a row does not
+// hold 8/16/32 cells); "vec1" / "vec2" = 128-bit kernels holding 8 / 16 line loads per lane in registers; "pipe4" /
+// "pipe6" = 128-bit kernels with a cp.async ring of 4 / 6 chunks per warp in shared memory. Default: see kDefaultVariant
+// (measured in profiles/README.md).
+constexpr int kDefaultVariant = 1;
 static int kernel_variant() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("OGN_KERNELS");
-        v = 1;
+        v = kDefaultVariant;
         if (e && !strcmp(e, "scalar")) v = 0;
+        else if (e && !strcmp(e, "vec1")) v = 1;
         else if (e && !strcmp(e, "vec2")) v = 2;
+        else if (e && !strcmp(e, "pipe4")) v = 4;
+        else if (e && !strcmp(e, "pipe6")) v = 6;
     }
     return v;
 }
@@ -815,18 +824,47 @@ static int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
     return e ? atoi(e) : dflt;
 }
-static int vec_threads() { // experiment knob: threads per block of the 128-bit kernels (a multiple of 32, at most 256)
+static int vec_threads() { // threads per block of the 128-bit kernels (a multiple of 32, at most 256); OGN_VEC_THREADS overrides
     static int v = 0;
-    if (!v) { v = env_int("OGN_VEC_THREADS", kThreads); if (v < 32 || v > kThreads || v % 32) v = kThreads; }
+    if (!v) {
+        v = env_int("OGN_VEC_THREADS", kernel_variant() >= 4 ? 128 : kThreads);
+        if (v < 32 || v > kThreads || v % 32) v = kThreads;
+    }
     return v;
 }
-static int pred_minb() { static int v = -1; if (v < 0) v = env_int("OGN_PRED_MINB", 1); return v; }
+static size_t ring_bytes(int threads) { // cp.async ring: D stages x 8 lines x 32 lanes x 16 bytes per warp
+    const int D = kernel_variant() >= 4 ? kernel_variant() : 0;
+    return (size_t)(threads / 32) * D * 4096;
+}
+
+} // extern "C"
+// <<<>>> with dynamic shared memory above the 48 KB default opted in once per kernel
+template <typename... P, typename... A>
+static void launch_k(void (*k)(P...), dim3 grid, int threads, size_t smem, cudaStream_t st, A... a) {
+    if (smem > 48u * 1024u) {
+        static std::mutex mtx;
+        static std::set<const void *> done;
+        std::lock_guard<std::mutex> lock(mtx);
+        if (done.insert((const void *)k).second)
+            cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    k<<<grid, threads, smem, st>>>(a...);
+}
+extern "C" {
 
 #define OGN_DISPATCH_Z(Z_, CALL)                     \
     switch (Z_) {                                    \
     case 8: { constexpr int Z = 8; CALL; } break;    \
     case 16: { constexpr int Z = 16; CALL; } break;  \
     default: { constexpr int Z = 32; CALL; } break;  \
+    }
+// CALL sees the compile-time constants Z, NCH (register batch depth) and D (cp.async ring depth, 0 = registers)
+#define OGN_DISPATCH_VEC(Z_, CALL)                                                              \
+    switch (kernel_variant()) {                                                                 \
+    case 2: { constexpr int NCH = 2, D = 0; OGN_DISPATCH_Z(Z_, CALL); } break;                  \
+    case 4: { constexpr int NCH = 1, D = 4; OGN_DISPATCH_Z(Z_, CALL); } break;                  \
+    case 6: { constexpr int NCH = 1, D = 6; OGN_DISPATCH_Z(Z_, CALL); } break;                  \
+    default: { constexpr int NCH = 1, D = 0; OGN_DISPATCH_Z(Z_, CALL); } break;                 \
     }
 
 int ogn_sc_forward(const ogn_fwd_args *args, int Hx, int Hy, int Hz, int x0, int x1, int batch, int *hidden_cs, int *hidden_cs2,
@@ -843,11 +881,8 @@ int ogn_sc_forward(const ogn_fwd_args *args, int Hx, int Hy, int Hz, int x0, int
     if (vecOk) {
         const int vt = vec_threads();
         dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
-        if (kernel_variant() == 1) {
-            OGN_DISPATCH_Z(Hz, (vec::k_sc_forward_v<Z, 1><<<grid, vt, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, hidden_cs, hidden_cs2)));
-        } else {
-            OGN_DISPATCH_Z(Hz, (vec::k_sc_forward_v<Z, 2><<<grid, vt, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, hidden_cs, hidden_cs2)));
-        }
+        OGN_DISPATCH_VEC(Hz, (launch_k(vec::k_sc_forward_v<Z, NCH, D>, grid, vt, ring_bytes(vt), st, *args, Hx, Hy, x0, npacks, ppr,
+                                       hidden_cs, hidden_cs2)));
         return launch_status();
     }
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);
@@ -873,11 +908,8 @@ int ogn_sc_learn(const ogn_learn_args *args, const int *hidden_cs, const int *hi
         int2 *work = (int2 *)args->work;
         unsigned *cnt = args->work_counters;
         if (phase != OGN_LEARN_UPDATE) {
-            if (kernel_variant() == 1) {
-                OGN_DISPATCH_Z(Vz, (vec::k_sc_recon_v<Z, 1><<<grid, vt, 0, st>>>(*args, hidden_cs, vx0, npacks, ppr, work, cnt)));
-            } else {
-                OGN_DISPATCH_Z(Vz, (vec::k_sc_recon_v<Z, 2><<<grid, vt, 0, st>>>(*args, hidden_cs, vx0, npacks, ppr, work, cnt)));
-            }
+            OGN_DISPATCH_VEC(Vz, (launch_k(vec::k_sc_recon_v<Z, NCH, D>, grid, vt, ring_bytes(vt), st, *args, hidden_cs, vx0, npacks, ppr,
+                                           work, cnt)));
             int e = launch_status();
             if (e || phase == OGN_LEARN_RECONSTRUCT) return e;
         }
@@ -913,14 +945,8 @@ int ogn_pred_step(const ogn_pred_args *args, int Hx, int Hy, int Hz, int x0, int
     if (vecOk) {
         const int vt = vec_threads();
         dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
-#define OGN_PRED_V(NCH_, MINB_)                                                                                                      \
-    OGN_DISPATCH_Z(Hz, (vec::k_pred_step_v<Z, NCH_, MINB_><<<grid, vt, 0, st>>>(*args, Hx, Hy, x0, npacks, ppr, learn, activate, target_cs, \
-                                                                            alpha, activations, hidden_cs)))
-        if (kernel_variant() == 2) { OGN_PRED_V(2, 1); }
-        else if (pred_minb() == 3) { OGN_PRED_V(1, 3); }
-        else if (pred_minb() == 4) { OGN_PRED_V(1, 4); }
-        else { OGN_PRED_V(1, 1); }
-#undef OGN_PRED_V
+        OGN_DISPATCH_VEC(Hz, (launch_k(vec::k_pred_step_v<Z, NCH, 1, D>, grid, vt, ring_bytes(vt), st, *args, Hx, Hy, x0, npacks, ppr,
+                                       learn, activate, target_cs, alpha, activations, hidden_cs)));
         return launch_status();
     }
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);

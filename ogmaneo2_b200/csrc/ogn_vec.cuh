@@ -115,6 +115,140 @@ __device__ __forceinline__ void add_delta(unsigned om, int sub, float *wl, const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// cp.async ring (template parameter D > 0 of the kernels): instead of holding a batch of lines in registers, every lane
+// copies "its" 16 bytes of each line straight into a private slice of shared memory (cp.async.cg, L2 -> smem, no
+// registers) and keeps D chunks of 8 lines in flight; a chunk is summed, in slot order, as soon as it has landed and its
+// stage is refilled with the chunk D ahead. One warp therefore has up to D * 4 KB in flight on its own, so a column's
+// whole field (11 chunks at radius 4) is covered by ~2 memory round trips instead of 11: short waves, no tail when a
+// sharded launch has only a couple of waves of work. Lanes only ever read back bytes they copied themselves, so
+// cp.async.wait_group is the only synchronisation. Ring layout per warp: [stage][slot j][lane] float4 (conflict-free).
+__device__ __forceinline__ void cp_async16(float4 *smem, const float *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Like SlotWalker, but the CSDR read of a chunk is handed out as a (meta, value) pair whose value the caller consumes
+// later: the reads of the first D chunks go out together instead of one L2 round trip each. Descriptor = meta + cv.
+struct SlotWalkerP {
+    struct Pending { unsigned meta; int cv; };
+    const int *cs;
+    int lx, lyU, nyU, nxv, n, Vy, Vz;
+    int s, dx, dy;
+    __device__ __forceinline__ void init(const int *cs_, const PackCtx &c, int Vy_, int Vz_, int sub) {
+        cs = cs_; lx = c.lx; lyU = c.lyU; nyU = c.nyU; n = c.nslotsU; nxv = n / max(nyU, 1); Vy = Vy_; Vz = Vz_;
+        s = sub; dx = s / max(nyU, 1); dy = s - dx * nyU;
+    }
+    __device__ __forceinline__ Pending fetch() {
+        const bool in = s < n;
+        Pending p;
+        p.meta = (unsigned)((in ? s : n - 1) * Vz) | ((in ? (unsigned)dy : kNoDy) << kLineBits);
+        p.cv = __ldg(cs + (lx + (in ? dx : nxv - 1)) * Vy + lyU + (in ? dy : nyU - 1));
+        s += 8; dy += 8;
+        while (dy >= nyU) { dy -= nyU; ++dx; }
+        return p;
+    }
+};
+
+// queue the 8 line copies of one chunk into `stage` (already offset by the lane); returns the own-field mask of the chunk
+__device__ __forceinline__ unsigned issue_chunk(unsigned om, float4 *stage, const float *wl, unsigned d, const PackCtx &c) {
+    unsigned vm = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const unsigned dj = __shfl_sync(om, d, j, 8);
+        vm |= ((unsigned)((int)(dj >> kLineBits) - c.dlo) < (unsigned)c.dn ? 1u : 0u) << j;
+        cp_async16(stage + j * 32, wl + ((size_t)(dj & kLineMask) << 5));
+    }
+    return vm;
+}
+
+template <int D>
+__device__ __forceinline__ float4 gather_p(unsigned om, int sub, float4 *ring, const float *wl, const int *cs, const PackCtx &c, int Vy,
+                                           int Vz) {
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (c.nslotsU <= 0) return acc;
+    SlotWalkerP sw;
+    sw.init(cs, c, Vy, Vz, sub);
+    const int nch = (c.nslotsU + 7) >> 3;
+    unsigned vm[D];
+    SlotWalkerP::Pending pq[D];
+#pragma unroll
+    for (int st = 0; st < D; ++st) pq[st] = sw.fetch();
+    SlotWalkerP::Pending nxt = sw.fetch();
+#pragma unroll
+    for (int st = 0; st < D; ++st) {
+        vm[st] = 0;
+        if (st < nch) vm[st] = issue_chunk(om, ring + st * 256, wl, pq[st].meta + (unsigned)pq[st].cv, c);
+        cp_async_commit();
+    }
+    for (int ch0 = 0; ch0 < nch; ch0 += D) {
+#pragma unroll
+        for (int st = 0; st < D; ++st) {
+            const int ch = ch0 + st;
+            if (ch < nch) {
+                cp_async_wait<D - 1>();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 w = ring[(st * 8 + j) * 32];
+                    if ((vm[st] >> j) & 1u) { acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w; }
+                }
+                if (ch + D < nch) {
+                    vm[st] = issue_chunk(om, ring + st * 256, wl, nxt.meta + (unsigned)nxt.cv, c);
+                    nxt = sw.fetch();
+                }
+                cp_async_commit();
+            }
+        }
+    }
+    return acc;
+}
+
+template <int D>
+__device__ __forceinline__ void add_delta_p(unsigned om, int sub, float4 *ring, float *wl, const int *cs, const float4 &delta,
+                                            const PackCtx &c, int Vy, int Vz) {
+    if (c.nslotsU <= 0) return;
+    SlotWalkerP sw;
+    sw.init(cs, c, Vy, Vz, sub);
+    const int nch = (c.nslotsU + 7) >> 3;
+    unsigned dq[D];
+    SlotWalkerP::Pending pq[D];
+#pragma unroll
+    for (int st = 0; st < D; ++st) pq[st] = sw.fetch();
+    SlotWalkerP::Pending nxt = sw.fetch();
+#pragma unroll
+    for (int st = 0; st < D; ++st) {
+        dq[st] = pq[st].meta + (unsigned)pq[st].cv;
+        if (st < nch) (void)issue_chunk(om, ring + st * 256, wl, dq[st], c);
+        cp_async_commit();
+    }
+    for (int ch0 = 0; ch0 < nch; ch0 += D) {
+#pragma unroll
+        for (int st = 0; st < D; ++st) {
+            const int ch = ch0 + st;
+            if (ch < nch) {
+                cp_async_wait<D - 1>();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned dj = __shfl_sync(om, dq[st], j, 8);
+                    if ((unsigned)((int)(dj >> kLineBits) - c.dlo) < (unsigned)c.dn) {
+                        float4 v = ring[(st * 8 + j) * 32];
+                        v.x += delta.x; v.y += delta.y; v.z += delta.z; v.w += delta.w;
+                        st_plain(wl + ((size_t)(dj & kLineMask) << 5), v);
+                    }
+                }
+                if (ch + D < nch) {
+                    dq[st] = nxt.meta + (unsigned)nxt.cv;
+                    (void)issue_chunk(om, ring + st * 256, wl, dq[st], c);
+                    nxt = sw.fetch();
+                }
+                cp_async_commit();
+            }
+        }
+    }
+}
+
 // First-max arg-max of the reference's forward scans (`if (sum > max)` from (0, -999999), SparseCoder.cpp:31-38,
 // Predictor.cpp:36-43) over the Z cells of a column spread over LC = Z/4 lanes x 4 cells. NaN never wins.
 template <int Z>
@@ -148,7 +282,9 @@ template <int Z> __device__ __forceinline__ PackId pack_id(int pack, int packsPe
 
 // ---------------------------------------------------------------------------------------------------------------
 // K2: SparseCoder::forward (SparseCoder.cpp:13-43), Hz = Z in {8, 16, 32}.
-template <int Z, int NCH>
+extern __shared__ float4 ogn_ring[]; // cp.async rings of the block's warps (D > 0): [warp][stage][slot][lane]
+
+template <int Z, int NCH, int D>
 __global__ void __launch_bounds__(kThreads)
 k_sc_forward_v(const __grid_constant__ ogn_fwd_args A, int Hx, int Hy, int x0, int npacks, int packsPerRow, int *__restrict__ out0,
                int *__restrict__ out1) {
@@ -158,6 +294,7 @@ k_sc_forward_v(const __grid_constant__ ogn_fwd_args A, int Hx, int Hy, int x0, i
     const unsigned om = octet_mask();
     const int member = blockIdx.y;
     const PackId id = pack_id<Z>(pack, packsPerRow, x0, Hy, sub);
+    float4 *ring = ogn_ring + (threadIdx.x >> 5) * (D * 256) + (threadIdx.x & 31);
 
     float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     for (int v = 0; v < A.nvl; ++v) {
@@ -166,7 +303,9 @@ k_sc_forward_v(const __grid_constant__ ogn_fwd_args A, int Hx, int Hy, int x0, i
         const PackCtx c = pack_ctx(rf, id.ox, id.q, id.p);
         const float *wl = vl.wf + (c.blk + (long long)member * vl.mstride) + sub * 4;
         const int *cs = vl.cs + (long long)member * rf.Vx * rf.Vy;
-        const float4 g = gather<true, NCH>(om, sub, wl, cs, c, rf.Vy, rf.Vz);
+        float4 g;
+        if constexpr (D > 0) g = gather_p<D>(om, sub, ring, wl, cs, c, rf.Vy, rf.Vz);
+        else g = gather<true, NCH>(om, sub, wl, cs, c, rf.Vy, rf.Vz);
         sum.x += g.x; sum.y += g.y; sum.z += g.z; sum.w += g.w;
     }
     const int best = column_argmax_fwd<Z>(om, id.hz0, sum);
@@ -180,7 +319,7 @@ k_sc_forward_v(const __grid_constant__ ogn_fwd_args A, int Hx, int Hy, int x0, i
 // ---------------------------------------------------------------------------------------------------------------
 // K6+K7+K8: Predictor::learn (Predictor.cpp:49-70), Predictor::forward (:13-47), inputCs -> inputCsPrev (:118-126),
 // Hz = Z in {8, 16, 32}.
-template <int Z, int NCH, int MINB>
+template <int Z, int NCH, int MINB, int D>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_pred_step_v(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int x0, int npacks, int packsPerRow, int learn, int activate,
               const int *__restrict__ target, float alpha, float *acts, int *__restrict__ hiddenCs) {
@@ -201,6 +340,7 @@ k_pred_step_v(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int x0, i
     const PackId id = pack_id<Z>(pack, packsPerRow, x0, Hy, sub);
     const long long col = (long long)member * Hx * Hy + id.ox * Hy + (id.colValid ? id.oy : Hy - 1);
     float *act4 = acts + col * Z + id.hz0;
+    float4 *ring = ogn_ring + (threadIdx.x >> 5) * (D * 256) + (threadIdx.x & 31);
 
     if (learn) {
         const int t = __ldg(target + col);
@@ -217,8 +357,10 @@ k_pred_step_v(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int x0, i
             if (!id.colValid) c.dn = 0;
             float *wl = vl.wf + (c.blk + (long long)member * vl.mstride) + sub * 4;
             const int *cs = vl.cs_prev + (long long)member * rf.Vx * rf.Vy;
-            add_delta<NCH>(om, sub, wl, cs, delta, c, rf.Vy, rf.Vz);
+            if constexpr (D > 0) add_delta_p<D>(om, sub, ring, wl, cs, delta, c, rf.Vy, rf.Vz);
+            else add_delta<NCH>(om, sub, wl, cs, delta, c, rf.Vy, rf.Vz);
         }
+        if (D > 0) __threadfence(); // the activate pass re-reads lines this lane just stored, through cp.async
     }
     if (!activate) return;
 
@@ -230,7 +372,9 @@ k_pred_step_v(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int x0, i
         const PackCtx c = pack_ctx(rf, id.ox, id.q, id.p);
         const float *wl = vl.wf + (c.blk + (long long)member * vl.mstride) + sub * 4;
         const int *cs = vl.cs + (long long)member * rf.Vx * rf.Vy;
-        const float4 g = gather<false, NCH>(om, sub, wl, cs, c, rf.Vy, rf.Vz);
+        float4 g;
+        if constexpr (D > 0) g = gather_p<D>(om, sub, ring, wl, cs, c, rf.Vy, rf.Vz);
+        else g = gather<false, NCH>(om, sub, wl, cs, c, rf.Vy, rf.Vz);
         sum.x += g.x; sum.y += g.y; sum.z += g.z; sum.w += g.w;
         count += c.dn * (c.nslotsU / max(c.nyU, 1)); // own field: nx * ny
     }
@@ -272,7 +416,7 @@ struct CoverWalker {
     }
 };
 
-template <int Z, int NCH>
+template <int Z, int NCH, int D>
 __global__ void __launch_bounds__(kThreads)
 k_sc_recon_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ hcsAll, int vx0, int npacks, int packsPerRow,
              int2 *__restrict__ work, unsigned *workCount) {
@@ -314,6 +458,53 @@ k_sc_recon_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ h
         cw.hcs = hcsAll + (long long)member * rf.Hx * rf.Hy;
         cw.hx0 = hx0; cw.hy0U = hy0U; cw.ncyU = ncyU; cw.n = ncovU; cw.vx = vx; cw.vyBase = vyBase;
         cw.k = sub; cw.ix = sub / ncyU; cw.iy = sub - cw.ix * ncyU;
+        if constexpr (D > 0) {
+            // cp.async ring: D chunks of 8 lines in flight per lane group (see gather_p)
+            float4 *ring = ogn_ring + (threadIdx.x >> 5) * (D * 256) + (threadIdx.x & 31);
+            const int nch = (ncovU + 7) >> 3;
+            unsigned long long dq[D];
+            unsigned vm[D];
+#pragma unroll
+            for (int st = 0; st < D; ++st) { dq[st] = cw.describe<Z>(rf); cw.advance(); }
+            unsigned long long nxt = cw.describe<Z>(rf);
+            cw.advance();
+            auto issue = [&](int st, unsigned long long d) {
+                unsigned m = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned long long dj = __shfl_sync(om, d, j, 8);
+                    m |= (unsigned)((dj >> pv) & 1ull) << j;
+                    cp_async16(ring + (st * 8 + j) * 32, wr + (dj & ~31ull));
+                }
+                return m;
+            };
+#pragma unroll
+            for (int st = 0; st < D; ++st) {
+                vm[st] = 0;
+                if (st < nch) vm[st] = issue(st, dq[st]);
+                cp_async_commit();
+            }
+            for (int ch0 = 0; ch0 < nch; ch0 += D) {
+#pragma unroll
+                for (int st = 0; st < D; ++st) {
+                    const int ch = ch0 + st;
+                    if (ch < nch) {
+                        cp_async_wait<D - 1>();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 w = ring[(st * 8 + j) * 32];
+                            if ((vm[st] >> j) & 1u) { sum.x += w.x; sum.y += w.y; sum.z += w.z; sum.w += w.w; }
+                        }
+                        if (ch + D < nch) {
+                            vm[st] = issue(st, nxt);
+                            nxt = cw.describe<Z>(rf);
+                            cw.advance();
+                        }
+                        cp_async_commit();
+                    }
+                }
+            }
+        } else {
         unsigned long long d[NCH];
 #pragma unroll
         for (int k = 0; k < NCH; ++k) { d[k] = cw.describe<Z>(rf); cw.advance(); }
@@ -334,6 +525,7 @@ k_sc_recon_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ h
 #pragma unroll
             for (int j = 0; j < 8 * NCH; ++j)
                 if ((vm >> j) & 1u) { sum.x += w[j].x; sum.y += w[j].y; sum.z += w[j].z; sum.w += w[j].w; }
+        }
         }
     }
     const float cnt = (float)ncov;
