@@ -1,8 +1,15 @@
 cd /root/repo
 mkdir -p gpurun_out
-python bench.py --size 184 --steps 100 --warmup 100 --no-cpu > gpurun_out/b184.log 2>&1; python -c "
-import json;d=json.loads(open('gpurun_out/b184.log').read().strip().split('\n')[-1]);print('with events ms/step',d['ms_per_step'], {k:v['ms_per_launch'] for k,v in d['roofline']['kernels'].items()})"
-OGN_BENCH_NOPROF=1 python bench.py --size 184 --steps 100 --warmup 100 --no-cpu 2>&1 | tail -3 | cut -c1-400
-python bench.py --size 184 --steps 30 --warmup 30 --no-cpu > gpurun_out/plain184.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,sm__cycles_elapsed.max,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -s 200 -c 40 --csv --log-file gpurun_out/launches_184.csv python bench.py --size 184 --steps 30 --warmup 30 --no-cpu > gpurun_out/ncu184.log 2>&1
-tail -2 gpurun_out/launches_184.csv | cut -c1-300
+show() { tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('N=%d steps/s %.1f ms/step %.3f e2e %.1f step_frac %.3f upd %s'%(d['n_gpus'],d['value'],d['ms_per_step'],d['e2e']['value'],r['step_frac'],r['sc_pairs_rewritten_per_step']), ' '.join('%s %.3fms %.0fGB/s'%(k,v['ms_per_launch'],v['achieved_gbs'] or 0) for k,v in r['kernels'].items()))
+for i,x in enumerate(d.get('ranks') or []): print('   rank',i,' '.join('%s=%.3f'%(k,v) for k,v in x.items() if v is not None))"; }
+python -m pytest tests -m gpu -x -q > gpurun_out/tests.log 2>&1; tail -5 gpurun_out/tests.log
+run1() { name=$1; shift; env "$@" python bench.py --steps 100 --warmup 100 --no-cpu > gpurun_out/n1_$name.log 2>&1; echo $name "$@"; cat gpurun_out/n1_$name.log | show; }
+run1 side1 OGN_SIDE_STREAM=1
+run1 side0 OGN_SIDE_STREAM=0
+N=2
+run() { name=$1; shift; env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 100 --warmup 100 --no-cpu > gpurun_out/n${N}_$name.log 2>&1; echo $name "$@"; cat gpurun_out/n${N}_$name.log | show; }
+run side1 OGN_SIDE_STREAM=1
+run side0 OGN_SIDE_STREAM=0

@@ -51,7 +51,10 @@ public:
     void initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize, const std::vector<VisibleLayerDesc> &visibleLayerDescs,
                           int batch, int member);
     // learn (optional) + activate (optional) as ONE kernel launch on device-resident CSDRs (int32 [member][columns]).
-    void stepDevice(ComputeSystem &cs, bool learn, const int *targetCsDevice, bool activate, const int *const *inputCsDevice);
+    // deferExchange (sharded + peer exchange only): queue the all-gather of the new hiddenCs on the side stream; the next
+    // exchange, getHiddenCs() and ComputeSystem::synchronize() wait for it
+    void stepDevice(ComputeSystem &cs, bool learn, const int *targetCsDevice, bool activate, const int *const *inputCsDevice,
+                    bool deferExchange = false);
     const int *hiddenCsDevice() const;
     void readFromStream(std::istream &is, ComputeSystem &cs);
     void setState(const IntBuffer &hiddenCs, const std::vector<IntBuffer> &inputCsPrev);

@@ -30,6 +30,34 @@ DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
     if (const char *g = std::getenv("OGN_L2_FETCH_GRANULARITY")) // experiment knob: 32 / 64 / 128 (a hint to the driver)
         cudaCheck(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g)), "cudaLimitMaxL2FetchGranularity");
     cudaCheck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    cudaCheck(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate(side)");
+    cudaCheck(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming), "cudaEventCreate");
+    cudaCheck(cudaEventCreateWithFlags(&evLearn, cudaEventDisableTiming), "cudaEventCreate");
+    cudaCheck(cudaEventCreateWithFlags(&evExchange, cudaEventDisableTiming), "cudaEventCreate");
+    if (const char *e = std::getenv("OGN_SIDE_STREAM")) useSide = std::atoi(e) != 0; // 0: everything on one stream
+}
+
+void DeviceContext::forkSide() {
+    cudaCheck(cudaEventRecord(evFork, stream), "cudaEventRecord");
+    cudaCheck(cudaStreamWaitEvent(side, evFork, 0), "cudaStreamWaitEvent");
+}
+void DeviceContext::learnQueued() {
+    cudaCheck(cudaEventRecord(evLearn, side), "cudaEventRecord");
+    learnPending = true;
+}
+void DeviceContext::exchangeQueued() {
+    cudaCheck(cudaEventRecord(evExchange, side), "cudaEventRecord");
+    exchangePending = true;
+}
+void DeviceContext::joinLearn() {
+    if (!learnPending) return;
+    cudaCheck(cudaStreamWaitEvent(stream, evLearn, 0), "cudaStreamWaitEvent");
+    learnPending = false;
+}
+void DeviceContext::joinExchange() {
+    if (!exchangePending) return;
+    cudaCheck(cudaStreamWaitEvent(stream, evExchange, 0), "cudaStreamWaitEvent");
+    exchangePending = false;
 }
 
 // ---- peer arena --------------------------------------------------------------------------------------------------
@@ -78,8 +106,13 @@ void DeviceContext::arenaAttach(const void *handles64, int world) {
     arena->attached = true;
 }
 
-void DeviceContext::peerAllGather(int *buffer, int countPerRank) {
+void DeviceContext::peerAllGather(int *buffer, int countPerRank, bool deferred) {
     PeerArena &a = *arena;
+    deferred = deferred && useSide;
+    // exchanges complete in the same order on every rank: an earlier deferred one is joined before the next is queued
+    cudaStream_t st = stream;
+    if (deferred) { forkSide(); st = side; }
+    else joinExchange();
     if (!a.attached) throw std::runtime_error("ogmaneo-b200: peer exchange used before ogn_peer_attach");
     if (!inArena(buffer)) throw std::runtime_error("ogmaneo-b200: peer all-gather of a buffer outside the exchange arena");
     ogn_peer_table t;
@@ -90,7 +123,8 @@ void DeviceContext::peerAllGather(int *buffer, int countPerRank) {
         const char *e = std::getenv("OGN_PEER_TIMEOUT_MS");
         return (unsigned long long)(e ? std::atoll(e) : 5000) * 1000000ull;
     }();
-    kernelCheck(ogn_peer_allgather(&t, buffer - a.base, countPerRank, ++a.epoch, timeoutNs, a.errDev, stream), "peer_allgather");
+    kernelCheck(ogn_peer_allgather(&t, buffer - a.base, countPerRank, ++a.epoch, timeoutNs, a.errDev, st), "peer_allgather");
+    if (deferred) exchangeQueued();
 }
 
 unsigned long long DeviceContext::peerTakeWaitNs() {
@@ -116,6 +150,10 @@ DeviceContext::~DeviceContext() {
     }
     for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : eventPool) cudaEventDestroy(e);
+    if (evFork) cudaEventDestroy(evFork);
+    if (evLearn) cudaEventDestroy(evLearn);
+    if (evExchange) cudaEventDestroy(evExchange);
+    if (side) cudaStreamDestroy(side);
     if (stream) cudaStreamDestroy(stream);
 }
 

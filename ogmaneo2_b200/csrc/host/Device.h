@@ -52,10 +52,28 @@ struct DeviceContext {
     bool inArena(const int *p) const { return arena && p >= arena->base && p < arena->base + arena->capInts; }
     void arenaExport(void *handle64) const;
     void arenaAttach(const void *handles64, int world);
-    void peerAllGather(int *buffer, int countPerRank);   // in-place all-gather of [world][countPerRank] ints, on `stream`
+    // in-place all-gather of [world][countPerRank] ints on `stream`; deferred = queue it on the side stream instead (the
+    // step's final output: nothing on `stream` needs it before the next exchange, which joins it)
+    void peerAllGather(int *buffer, int countPerRank, bool deferred = false);
     void peerCheck() const;                              // throws if a peer wait timed out
     unsigned long long peerTakeWaitNs();                 // device time spent waiting for other ranks since the last call (syncs)
-    void sync() const { cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize"); }
+    // Side stream: SparseCoder learn (reconstruction + update) of a step runs here, concurrently with the Predictors on
+    // `stream` (they touch disjoint weights; the two bandwidth-bound kernel chains fill each other's tails), and so does
+    // the deferred exchange of the step's output predictions. forkSide() makes the side stream wait for everything
+    // queued on `stream` so far; joinLearn()/joinExchange() make `stream` wait for the side work recorded last.
+    cudaStream_t side;
+    cudaEvent_t evFork, evLearn, evExchange;
+    bool learnPending = false, exchangePending = false, useSide = true;
+    void forkSide();
+    void learnQueued();     // call after queueing learn work on `side`
+    void exchangeQueued();  // call after queueing a deferred exchange on `side`
+    void joinLearn();
+    void joinExchange();
+    void joinSide() { joinLearn(); joinExchange(); }
+    void sync() const {
+        cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+        cudaCheck(cudaStreamSynchronize(side), "cudaStreamSynchronize(side)");
+    }
 
     // Launch accounting: counts are always kept; with profiling on, every launch is bracketed by two CUDA events on
     // `stream` and profileCollect() (after a sync) turns them into per-kind device time.
@@ -74,15 +92,16 @@ struct DeviceContext {
 struct LaunchScope {
     DeviceContext &c;
     int kind;
+    cudaStream_t st;
     cudaEvent_t a = nullptr;
-    LaunchScope(DeviceContext &ctx, int kind_) : c(ctx), kind(kind_) {
+    LaunchScope(DeviceContext &ctx, int kind_, cudaStream_t stream = nullptr) : c(ctx), kind(kind_), st(stream ? stream : ctx.stream) {
         c.launches[kind]++;
-        if (c.profiling) { a = c.takeEvent(); cudaCheck(cudaEventRecord(a, c.stream), "cudaEventRecord"); }
+        if (c.profiling) { a = c.takeEvent(); cudaCheck(cudaEventRecord(a, st), "cudaEventRecord"); }
     }
     ~LaunchScope() {
         if (a) {
             cudaEvent_t b = c.takeEvent();
-            cudaEventRecord(b, c.stream);
+            cudaEventRecord(b, st);
             c.recs.push_back(DeviceContext::Rec{a, b, kind});
         }
     }

@@ -218,12 +218,17 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const std::vector<const IntBuffer *>
         for (size_t p = 0; p < pLayers[l].size(); p++) {
             if (!pLayers[l][p]) continue;
             const int *target = l == 0 ? m.histories[0][p].slot(0) : m.histories[l][0].slot((int)p);
-            pLayers[l][p]->stepDevice(cs, learnEnabled, target, true, fb);
+            // layer 0's predictions are the step's output: nothing queued later in this step reads them, so their
+            // exchange between shards is deferred to the side stream
+            pLayers[l][p]->stepDevice(cs, learnEnabled, target, true, fb, l == 0);
         }
         if (l == 0)
             for (size_t p = 0; p < aLayers.size(); p++)
                 if (aLayers[p]) aLayers[p]->stepDevice(cs, fb, m.histories[0][p].slot(0), reward, learnEnabled, mimic);
     }
+    // SparseCoder learn ran on the side stream, concurrently with the Predictors above: everything queued on the main
+    // stream from here on (the next step, getters, copies) is ordered behind it
+    ctx.joinLearn();
 }
 
 void Hierarchy::step(ComputeSystem &cs, const std::vector<const IntBuffer *> &inputCs, bool learnEnabled, float reward, bool mimic) {

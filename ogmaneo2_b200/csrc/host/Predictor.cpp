@@ -18,6 +18,7 @@ Predictor &Predictor::operator=(const Predictor &o) {
         const Impl &s = *o.impl;
         DeviceContext &ctx = *s.ctx;
         cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+        ctx.joinSide();
         impl->ctx = s.ctx; impl->batch = s.batch; impl->x0 = s.x0; impl->x1 = s.x1; impl->world = s.world;
         impl->prevCur = s.prevCur; impl->csDirty = s.csDirty; impl->actDirty = s.actDirty; impl->prevDirty = s.prevDirty;
         impl->wDirty = s.wDirty;
@@ -71,7 +72,8 @@ void Predictor::initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize_, con
 }
 
 // Predictor::learn (Predictor.cpp:129-135) followed by Predictor::activate (:111-127) as one launch (K6+K7+K8)
-void Predictor::stepDevice(ComputeSystem &cs, bool learn, const int *targetDev, bool activate, const int *const *inputDev) {
+void Predictor::stepDevice(ComputeSystem &cs, bool learn, const int *targetDev, bool activate, const int *const *inputDev,
+                           bool deferExchange) {
     Impl &m = *impl;
     DeviceContext &ctx = *m.ctx;
     const int nvl = (int)visibleLayerDescs.size();
@@ -100,7 +102,7 @@ void Predictor::stepDevice(ComputeSystem &cs, bool learn, const int *targetDev, 
         m.prevCur = 1 - m.prevCur;
         m.csDirty = m.actDirty = m.prevDirty = true;
         if (m.world > 1) {
-            if (ctx.arena && ctx.inArena(m.hiddenCs.ptr())) ctx.peerAllGather(m.hiddenCs.ptr(), (m.x1 - m.x0) * hiddenSize.y);
+            if (ctx.arena && ctx.inArena(m.hiddenCs.ptr())) ctx.peerAllGather(m.hiddenCs.ptr(), (m.x1 - m.x0) * hiddenSize.y, deferExchange);
             else if (cs.allGather) cs.allGather(cs.allGatherUser, m.hiddenCs.ptr(), (m.x1 - m.x0) * hiddenSize.y, (void *)ctx.stream);
             else throw std::runtime_error("ogmaneo-b200: shardWorld > 1 needs ComputeSystem::allGather or peerExchange");
         }
@@ -134,6 +136,7 @@ const IntBuffer &Predictor::getHiddenCs() const {
     Impl &m = *impl;
     if (m.csDirty) {
         cudaCheck(cudaSetDevice(m.ctx->device), "cudaSetDevice");
+        m.ctx->joinExchange(); // a deferred exchange of this CSDR may still be running on the side stream
         hiddenCs.resize(m.hiddenCs.size());
         m.hiddenCs.download(hiddenCs.data(), hiddenCs.size(), m.ctx->stream);
         m.ctx->sync();

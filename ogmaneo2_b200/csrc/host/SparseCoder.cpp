@@ -114,6 +114,11 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
                                       ctx.stream), "hiddenCs D2D");
     }
     if (learnEnabled) {
+        // learn touches only this layer's weights: queue it on the side stream, behind everything queued so far, so that
+        // it overlaps whatever the caller queues next on the main stream (upper layers, the Predictors). Hierarchy::step
+        // joins it at the end of the step; the host-facing step() synchronises both streams.
+        cudaStream_t lst = ctx.stream;
+        if (ctx.useSide) { ctx.forkSide(); lst = ctx.side; }
         int v = 0;
         while (v < nvl) { // one launch per run of visible layers with the same shape and radius
             int e = v + 1;
@@ -131,16 +136,17 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
                 l.f_mstride = w.fCount(); l.r_mstride = w.rCount();
             }
             // reconstruction (or the whole fused learn when the 128-bit path does not apply), then the work-list update
-            { LaunchScope ls(ctx, kScLearn);
-            kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_RECONSTRUCT, ctx.stream),
+            { LaunchScope ls(ctx, kScLearn, lst);
+            kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_RECONSTRUCT, lst),
                         "sc_learn"); }
             if (ogn_sc_learn_is_split(&la)) {
-                LaunchScope ls(ctx, kScUpdate);
-                kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_UPDATE, ctx.stream),
+                LaunchScope ls(ctx, kScUpdate, lst);
+                kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_UPDATE, lst),
                             "sc_update");
             }
             v = e;
         }
+        if (ctx.useSide) ctx.learnQueued();
         std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
         m.reconDirty = true;
     }
