@@ -39,6 +39,7 @@ METRIC = "hierarchy_steps_per_s_learn_on"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel at the default workload (C4 512x512), from the
 # `ncu --set full` capture summarised in profiles/README.md (filled in from the capture; None = not captured)
 TRAFFIC = {}
+PROF_PERIOD = 8
 UNIT = "steps/s"
 
 
@@ -311,7 +312,8 @@ def main():
     barrier()
     for l in range(len(cfg["layerDescs"])):
         h.takeSCUpdateCount(l)
-    h.profileEnable(os.environ.get("OGN_BENCH_NOPROF") != "1")
+    # per-kernel CUDA events on every PROF_PERIOD-th step of the timed region (every step would cost ~8% of a sharded step)
+    h.profileEnable(os.environ.get("OGN_BENCH_NOPROF") != "1", period=PROF_PERIOD)
     if peer:
         h.peerTakeWaitNs()
     clocks = ClockSampler(local_rank) if rank == 0 else None
@@ -415,7 +417,8 @@ def main():
                    if world > 1 else "single GPU",
                    "l2": "per-step weight traffic (GBs) far exceeds the 126 MB L2; no flush needed" if args.workload == "c4"
                    else "weights exceed L2" if args.workload == "c2" else "L2-resident (latency-bound config)",
-                   "init": "device counter-hash" if cfg["device_init"] else "std::mt19937 in reference order"})
+                   "init": "device counter-hash" if cfg["device_init"] else "std::mt19937 in reference order",
+                   "kernel_timing": f"CUDA events around every kernel launch of every {PROF_PERIOD}th step of the timed region"})
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": config, "roofline": roofline, "cpu_baseline": cpu,

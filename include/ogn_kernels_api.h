@@ -152,7 +152,9 @@ int ogn_sc_learn_is_split(const ogn_learn_args *args_host);
 
 /* K6+K7+K8 — Predictor::learn (Predictor.cpp:49-70, deltaOHVs SparseMatrix.cpp:488-501), then Predictor::forward
  * (Predictor.cpp:13-47), then inputCs -> inputCsPrev (Predictor.cpp:118-126), over hidden x in [x0,x1).
- * learn != 0 requires target_cs. activations: [member][Hx][Hy][Hz] in/out (read by learn, rewritten by forward). */
+ * learn != 0 requires target_cs. activations: [member][Hx][Hy][Hz] in/out (read by learn, rewritten by forward).
+ * activate: 0 = learn only; 1 = activate and copy the inputs (all of them, whatever [x0,x1) is) to cs_prev_out;
+ * 2 = activate without the copy (a launch over part of the rows whose sibling launch does the copy). */
 int ogn_pred_step(const ogn_pred_args *args_host, int Hx, int Hy, int Hz, int x0, int x1, int batch, int learn, int activate,
                   const int *target_cs, float alpha, float *activations, int *hidden_cs, void *stream);
 

@@ -171,6 +171,7 @@ void DeviceContext::profileCollect() {
         float ms = 0.0f;
         cudaCheck(cudaEventElapsedTime(&ms, r.a, r.b), "cudaEventElapsedTime");
         kernelMs[r.kind] += ms;
+        timedLaunches[r.kind]++;
         eventPool.push_back(r.a); eventPool.push_back(r.b);
     }
     recs.clear();
@@ -178,7 +179,8 @@ void DeviceContext::profileCollect() {
 
 void DeviceContext::profileReset() {
     profileCollect();
-    for (int k = 0; k < kKernelKinds; k++) { launches[k] = 0; kernelMs[k] = 0.0; }
+    for (int k = 0; k < kKernelKinds; k++) { launches[k] = 0; timedLaunches[k] = 0; kernelMs[k] = 0.0; }
+    profileStep = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -443,6 +445,9 @@ int ComputeSystem::getNumThreads() { return g_numThreads; }
 detail::DeviceContext &ComputeSystem::context() {
     if (!ctx) {
         ctx = std::make_shared<detail::DeviceContext>(device);
+        // the side stream pays off when a step is short and has exchanges to hide (sharded layers); on one GPU the kernel
+        // chains are bandwidth-bound either way and a single stream keeps the per-kernel timings undisturbed
+        if (!std::getenv("OGN_SIDE_STREAM")) ctx->useSide = shardWorld > 1;
         if (peerExchange && shardWorld > 1) {
             const char *e = std::getenv("OGN_PEER_ARENA_MB");
             ctx->arenaCreate((size_t)(e ? std::atoll(e) : 64) << 20, shardRank, shardWorld);

@@ -78,6 +78,13 @@ struct DeviceContext {
     // Launch accounting: counts are always kept; with profiling on, every launch is bracketed by two CUDA events on
     // `stream` and profileCollect() (after a sync) turns them into per-kind device time.
     bool profiling = false;
+    // Bracketing every launch with events costs stream time (about 4 us per kernel on a sharded 0.3 ms step), so only
+    // every profilePeriod-th Hierarchy::step is timed; timedLaunches counts the launches kernelMs sums over.
+    int profilePeriod = 1;
+    long long profileStep = 0;
+    bool sampleThis = true;
+    void beginStep() { sampleThis = profiling && (profileStep++ % (profilePeriod > 0 ? profilePeriod : 1)) == 0; }
+    long long timedLaunches[kKernelKinds] = {0, 0, 0, 0, 0, 0};
     long long launches[kKernelKinds] = {0, 0, 0, 0, 0, 0};
     double kernelMs[kKernelKinds] = {0, 0, 0, 0, 0, 0};
     struct Rec { cudaEvent_t a, b; int kind; };
@@ -96,7 +103,7 @@ struct LaunchScope {
     cudaEvent_t a = nullptr;
     LaunchScope(DeviceContext &ctx, int kind_, cudaStream_t stream = nullptr) : c(ctx), kind(kind_), st(stream ? stream : ctx.stream) {
         c.launches[kind]++;
-        if (c.profiling) { a = c.takeEvent(); cudaCheck(cudaEventRecord(a, st), "cudaEventRecord"); }
+        if (c.profiling && c.sampleThis) { a = c.takeEvent(); cudaCheck(cudaEventRecord(a, st), "cudaEventRecord"); }
     }
     ~LaunchScope() {
         if (a) {

@@ -297,15 +297,18 @@ int ogn_profile_enable(void *hh, int on) {
         detail::DeviceContext &c = ((Handle *)hh)->cs.context();
         c.profileReset();
         c.profiling = on != 0;
+        c.profilePeriod = on > 1 ? on : 1;
+        c.sampleThis = c.profiling;
     });
 }
-int ogn_profile_read(void *hh, double *ms, int64_t *launches) {
+int ogn_profile_read(void *hh, double *ms, int64_t *launches, int64_t *timed_launches) {
     return guard([&] {
         detail::DeviceContext &c = ((Handle *)hh)->cs.context();
         c.profileCollect();
         for (int k = 0; k < detail::kKernelKinds; k++) {
             if (ms) ms[k] = c.kernelMs[k];
             if (launches) launches[k] = c.launches[k];
+            if (timed_launches) timed_launches[k] = c.timedLaunches[k];
         }
     });
 }

@@ -173,6 +173,7 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const std::vector<const IntBuffer *>
     const int L = (int)scLayers.size(), NI = (int)inputSizes.size();
     if ((hostIn ? hostIn->size() : devIn->size()) != (size_t)NI) throw std::invalid_argument("ogmaneo-b200: wrong number of input CSDRs");
 
+    ctx.beginStep();
     ticks[0] = 0;
     // K1: inputs -> front of the layer-0 history rings
     if (hostIn) cudaCheck(cudaEventSynchronize(m.inFree), "cudaEventSynchronize");

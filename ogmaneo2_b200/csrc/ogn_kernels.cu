@@ -370,7 +370,7 @@ k_pred_step(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int Hz, int
     constexpr int P = Pack<G>::P, GP = Pack<G>::GP;
     const int member = blockIdx.y;
     // K8: every thread of the grid helps copying the inputs into the *other* inputCsPrev buffer (never read here)
-    if (activate) {
+    if (activate == 1) {
         const int tid = blockIdx.x * kThreads + threadIdx.x, nth = gridDim.x * kThreads;
         for (int v = 0; v < A.nvl; ++v) {
             if (!A.vl[v].cs_prev_out) continue;

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
 k_pred_step_v(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int x0, int npacks, int packsPerRow, int learn, int activate,
               const int *__restrict__ target, float alpha, float *acts, int *__restrict__ hiddenCs) {
     const int member = blockIdx.y;
-    if (activate) { // K8: the grid copies the inputs into the *other* inputCsPrev buffer (never read by this launch)
+    if (activate == 1) { // K8: the grid copies the inputs into the *other* inputCsPrev buffer (never read by this launch)
         const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
         for (int v = 0; v < A.nvl; ++v) {
             if (!A.vl[v].cs_prev_out) continue;

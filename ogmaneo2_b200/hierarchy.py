@@ -51,7 +51,7 @@ _PRODUCT_SIGS = {
     "peer_attach": (C.c_int, [_VP, C.c_void_p, C.c_int]),
     "peer_take_wait_ns": (C.c_uint64, [_VP]),
     "profile_enable": (C.c_int, [_VP, C.c_int]),
-    "profile_read": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "profile_read": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 PRODUCT_API_NAMES = tuple(_PRODUCT_SIGS)
 
@@ -147,15 +147,19 @@ class Hierarchy(FlatHierarchy):
 
     KERNEL_KINDS = ("sc_forward", "sc_learn", "pred_step", "actor_forward", "actor_learn", "sc_update")
 
-    def profileEnable(self, on: bool = True):
-        self._chk(self.f.profile_enable(self.h, int(on)), "profile_enable")
+    def profileEnable(self, on=True, period: int = 1):
+        """Count launches; time (CUDA events) the launches of every period-th step."""
+        self._chk(self.f.profile_enable(self.h, (max(int(period), 1) if on else 0)), "profile_enable")
 
-    def profileRead(self) -> dict:
-        """{kind: (device ms, launches)} accumulated since profileEnable()."""
+    def profileRead(self, timed: bool = False) -> dict:
+        """{kind: (device ms over the timed launches, launches[, timed launches])} accumulated since profileEnable()."""
         ms = (C.c_double * len(self.KERNEL_KINDS))()
         n = (C.c_int64 * len(self.KERNEL_KINDS))()
-        self._chk(self.f.profile_read(self.h, ms, n), "profile_read")
-        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNEL_KINDS)}
+        nt = (C.c_int64 * len(self.KERNEL_KINDS))()
+        self._chk(self.f.profile_read(self.h, ms, n, nt), "profile_read")
+        if timed:
+            return {k: (ms[i], n[i], nt[i]) for i, k in enumerate(self.KERNEL_KINDS)}
+        return {k: (ms[i] * (n[i] / nt[i]) if nt[i] else 0.0, n[i]) for i, k in enumerate(self.KERNEL_KINDS)}
 
     def takeSCUpdateCount(self, l: int) -> int:
         return int(self.f.take_sc_update_count(self.h, l))
