@@ -53,8 +53,9 @@ public:
     // learn (optional) + activate (optional) as ONE kernel launch on device-resident CSDRs (int32 [member][columns]).
     // deferExchange (sharded + peer exchange only): queue the all-gather of the new hiddenCs on the side stream; the next
     // exchange, getHiddenCs() and ComputeSystem::synchronize() wait for it
+    // onSideStream: queue a learn-only pass on the ComputeSystem's side stream (the caller orders it)
     void stepDevice(ComputeSystem &cs, bool learn, const int *targetCsDevice, bool activate, const int *const *inputCsDevice,
-                    bool deferExchange = false);
+                    bool deferExchange = false, bool onSideStream = false);
     const int *hiddenCsDevice() const;
     void readFromStream(std::istream &is, ComputeSystem &cs);
     void setState(const IntBuffer &hiddenCs, const std::vector<IntBuffer> &inputCsPrev);

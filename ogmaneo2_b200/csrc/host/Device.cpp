@@ -34,6 +34,7 @@ DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
     cudaCheck(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evLearn, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evExchange, cudaEventDisableTiming), "cudaEventCreate");
+    cudaCheck(cudaEventCreateWithFlags(&evPredLearn, cudaEventDisableTiming), "cudaEventCreate");
     if (const char *e = std::getenv("OGN_SIDE_STREAM")) useSide = std::atoi(e) != 0; // 0: everything on one stream
 }
 
@@ -153,6 +154,7 @@ DeviceContext::~DeviceContext() {
     if (evFork) cudaEventDestroy(evFork);
     if (evLearn) cudaEventDestroy(evLearn);
     if (evExchange) cudaEventDestroy(evExchange);
+    if (evPredLearn) cudaEventDestroy(evPredLearn);
     if (side) cudaStreamDestroy(side);
     if (stream) cudaStreamDestroy(stream);
 }

@@ -62,7 +62,7 @@ struct DeviceContext {
     // the deferred exchange of the step's output predictions. forkSide() makes the side stream wait for everything
     // queued on `stream` so far; joinLearn()/joinExchange() make `stream` wait for the side work recorded last.
     cudaStream_t side;
-    cudaEvent_t evFork, evLearn, evExchange;
+    cudaEvent_t evFork, evLearn, evExchange, evPredLearn;
     bool learnPending = false, exchangePending = false, useSide = true;
     void forkSide();
     void learnQueued();     // call after queueing learn work on `side`

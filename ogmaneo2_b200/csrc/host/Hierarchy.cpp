@@ -190,6 +190,22 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const std::vector<const IntBuffer *>
     }
     if (hostIn) cudaCheck(cudaEventRecord(m.inFree, ctx.stream), "cudaEventRecord");
 
+    // Sharded layers: the learn pass of the layer-0 Predictors needs nothing this step produces (its target is the
+    // input just copied, its gather rows are last step's inputs), so it is hoisted to the side stream and runs while the
+    // main stream does the SparseCoder forward pass and its slab exchange; the activate pass follows on the main stream.
+    const bool hoistPredLearn = ctx.useSide && learnEnabled && !cs.replayRng;
+    bool predLearnPending = false;
+    if (hoistPredLearn) {
+        bool any = false;
+        for (size_t p = 0; p < pLayers[0].size(); p++) {
+            if (!pLayers[0][p]) continue;
+            if (!any) { ctx.forkSide(); any = true; }
+            pLayers[0][p]->stepDevice(cs, true, m.histories[0][p].slot(0), false, nullptr, false, true);
+        }
+        if (any) cudaCheck(cudaEventRecord(ctx.evPredLearn, ctx.side), "cudaEventRecord");
+        predLearnPending = any;
+    }
+
     updates.assign(L, 0);
     std::vector<const int *> ptrs;
     // forward (bottom-up) pass of the SparseCoders
@@ -221,7 +237,12 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const std::vector<const IntBuffer *>
             const int *target = l == 0 ? m.histories[0][p].slot(0) : m.histories[l][0].slot((int)p);
             // layer 0's predictions are the step's output: nothing queued later in this step reads them, so their
             // exchange between shards is deferred to the side stream
-            pLayers[l][p]->stepDevice(cs, learnEnabled, target, true, fb, l == 0);
+            const bool hoisted = l == 0 && hoistPredLearn;
+            if (hoisted && predLearnPending) {
+                cudaCheck(cudaStreamWaitEvent(ctx.stream, ctx.evPredLearn, 0), "cudaStreamWaitEvent");
+                predLearnPending = false;
+            }
+            pLayers[l][p]->stepDevice(cs, learnEnabled && !hoisted, target, true, fb, l == 0);
         }
         if (l == 0)
             for (size_t p = 0; p < aLayers.size(); p++)

@@ -73,7 +73,7 @@ void Predictor::initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize_, con
 
 // Predictor::learn (Predictor.cpp:129-135) followed by Predictor::activate (:111-127) as one launch (K6+K7+K8)
 void Predictor::stepDevice(ComputeSystem &cs, bool learn, const int *targetDev, bool activate, const int *const *inputDev,
-                           bool deferExchange) {
+                           bool deferExchange, bool onSideStream) {
     Impl &m = *impl;
     DeviceContext &ctx = *m.ctx;
     const int nvl = (int)visibleLayerDescs.size();
@@ -94,35 +94,11 @@ void Predictor::stepDevice(ComputeSystem &cs, bool learn, const int *targetDev, 
         consumeKernel2(cs, hiddenSize.x, hiddenSize.y);
         for (int v = 0; v < nvl; v++) consumeKernel1(cs, visibleLayerDescs[v].size.x * visibleLayerDescs[v].size.y);
     }
-    auto launch = [&](int xa, int xb, int act) {
-        if (xb <= xa) return;
-        LaunchScope ls(ctx, kPredStep);
-        kernelCheck(ogn_pred_step(&a, hiddenSize.x, hiddenSize.y, hiddenSize.z, xa, xb, m.batch, learn ? 1 : 0, act, targetDev, alpha,
-                                  m.acts.ptr(), m.hiddenCs.ptr(), ctx.stream), "pred_step");
-    };
-    if (activate && m.world > 1 && ctx.exchangePending) {
-        // The all-gather of the first visible layer's CSDR (the SparseCoder's hidden state) is still running on the side
-        // stream. Rows whose receptive field lies inside this rank's own slab of it do not need the neighbours' halo rows:
-        // they go first; the few boundary rows (and the copy of the full inputs) follow the exchange.
-        const Geometry &g = *m.ws.sets[0].geo;
-        int va = 0, vb = 0;
-        slabOf(g.Vx, cs.shardRank, cs.shardWorld, va, vb);
-        int i0 = m.x0, i1 = m.x1;
-        while (i0 < m.x1 && !(g.lox[i0] >= va && g.lox[i0] + g.nx[i0] <= vb)) i0++;
-        i1 = i0;
-        while (i1 < m.x1 && g.lox[i1] >= va && g.lox[i1] + g.nx[i1] <= vb) i1++;
-        if (i0 == m.x0 && i1 == m.x1) { // no boundary rows (radius 0): only the copy of the full inputs needs the exchange
-            ctx.joinExchange();
-            launch(m.x0, m.x1, 1);
-        } else {
-            const bool low = i0 > m.x0;
-            launch(i0, i1, 2);
-            ctx.joinExchange();
-            launch(m.x0, i0, low ? 1 : 2);
-            launch(i1, m.x1, low ? 2 : 1);
-        }
-    } else
-        launch(m.x0, m.x1, activate ? 1 : 0);
+    // onSideStream: a learn-only pass the caller hoisted to the side stream (see Hierarchy::step)
+    cudaStream_t st = (onSideStream && ctx.useSide && !activate) ? ctx.side : ctx.stream;
+    { LaunchScope ls(ctx, kPredStep, st);
+    kernelCheck(ogn_pred_step(&a, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, learn ? 1 : 0, activate ? 1 : 0,
+                              targetDev, alpha, m.acts.ptr(), m.hiddenCs.ptr(), st), "pred_step"); }
     if (learn) std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
     if (activate) {
         m.prevCur = 1 - m.prevCur;

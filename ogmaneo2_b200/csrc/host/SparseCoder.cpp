@@ -106,9 +106,7 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
     kernelCheck(ogn_sc_forward(&fa, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, out, sharded ? nullptr : copyOut,
                                ctx.stream), "sc_forward"); }
     if (sharded) {
-        // without a next layer to feed (copyOut) the only consumers queued after this are SparseCoder learn (side stream)
-        // and the Predictors, which start on their interior rows: the exchange goes to the side stream, off the main path
-        if (ctx.arena && ctx.inArena(out)) ctx.peerAllGather(out, (m.x1 - m.x0) * hiddenSize.y, copyOut == nullptr);
+        if (ctx.arena && ctx.inArena(out)) ctx.peerAllGather(out, (m.x1 - m.x0) * hiddenSize.y);
         else if (cs.allGather) cs.allGather(cs.allGatherUser, out, (m.x1 - m.x0) * hiddenSize.y, (void *)ctx.stream);
         else throw std::runtime_error("ogmaneo-b200: shardWorld > 1 needs ComputeSystem::allGather or peerExchange");
         if (copyOut)
