@@ -77,6 +77,11 @@ public:
     const std::vector<std::unique_ptr<Actor>> &getALayers() const { return aLayers; }
 
     // --- extensions (not in the reference) ---
+    // step() on raw host pointers (input i holds inputSizes[i].x * inputSizes[i].y * ensemble ints): what the C ABI calls,
+    // without building IntBuffers first
+    void stepHost(ComputeSystem &cs, const int *const *inputCs, bool learnEnabled = true, float reward = 0.0f, bool mimic = false);
+    // getPredictionCs(i) copied straight into out (pinned staging, no host mirror refresh); returns the column count
+    int copyPredictionCs(int i, int *out) const;
     // Same as step() but the inputs are already in device memory (int32, [member][columns] each) and nothing is copied
     // back: the whole step is asynchronous on cs' stream.
     void stepDevice(ComputeSystem &cs, const std::vector<const int *> &inputCsDevice, bool learnEnabled = true,
@@ -103,7 +108,7 @@ private:
 
     void initImpl(ComputeSystem &cs, const std::vector<Int3> &inputSizes, const std::vector<InputType> &inputTypes,
                   const std::vector<LayerDesc> &layerDescs, int batch, int member);
-    void stepImpl(ComputeSystem &cs, const std::vector<const IntBuffer *> *hostIn, const std::vector<const int *> *devIn,
+    void stepImpl(ComputeSystem &cs, const int *const *hostIn, const std::vector<const int *> *devIn,
                   bool learnEnabled, float reward, bool mimic);
 };
 } // namespace ogmaneo

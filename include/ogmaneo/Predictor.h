@@ -48,6 +48,7 @@ public:
     const FloatBuffer &getHiddenActivations() const; // private in the reference (Predictor.h:42)
     void getWeights(int i, std::vector<float> &out) const;
     const IntBuffer &getInputCsPrev(int i) const;
+    int copyHiddenCs(int *out) const; // getHiddenCs() straight into out (pinned staging); returns the column count
     void initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize, const std::vector<VisibleLayerDesc> &visibleLayerDescs,
                           int batch, int member);
     // learn (optional) + activate (optional) as ONE kernel launch on device-resident CSDRs (int32 [member][columns]).

@@ -101,15 +101,7 @@ void ogn_destroy(void *h) {
 int ogn_step(void *hh, const int *const *input_cs, int learn, float reward, int mimic) {
     return guard([&] {
         Handle *H = (Handle *)hh;
-        const std::vector<Int3> &sz = H->h.getInputSizes();
-        const int B = H->h.getEnsembleSize();
-        std::vector<IntBuffer> bufs(sz.size());
-        std::vector<const IntBuffer *> ptrs(sz.size());
-        for (size_t i = 0; i < sz.size(); i++) {
-            bufs[i].assign(input_cs[i], input_cs[i] + (size_t)sz[i].x * sz[i].y * B);
-            ptrs[i] = &bufs[i];
-        }
-        H->h.step(H->cs, ptrs, learn != 0, reward, mimic != 0);
+        H->h.stepHost(H->cs, input_cs, learn != 0, reward, mimic != 0);
     });
 }
 int ogn_step_device(void *hh, const int *const *input_cs_dev, int learn, float reward, int mimic) {
@@ -147,7 +139,7 @@ int ogn_get_prediction_cs(void *hh, int i, int *out) {
     guard([&] {
         Hierarchy &h = ((Handle *)hh)->h;
         if (h.getALayers()[i] == nullptr && h.getPLayers(0)[i] == nullptr) return;
-        n = copyOut(h.getPredictionCs(i), out);
+        n = h.copyPredictionCs(i, out);
     });
     return n;
 }

@@ -165,13 +165,13 @@ void Hierarchy::initRandomEnsemble(ComputeSystem &cs, const std::vector<unsigned
 int Hierarchy::getEnsembleSize() const { return impl ? impl->batch : 0; }
 
 // Hierarchy.cpp:192-285
-void Hierarchy::stepImpl(ComputeSystem &cs, const std::vector<const IntBuffer *> *hostIn, const std::vector<const int *> *devIn,
+void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std::vector<const int *> *devIn,
                          bool learnEnabled, float reward, bool mimic) {
     Impl &m = *impl;
     DeviceContext &ctx = *m.ctx;
     cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
     const int L = (int)scLayers.size(), NI = (int)inputSizes.size();
-    if ((hostIn ? hostIn->size() : devIn->size()) != (size_t)NI) throw std::invalid_argument("ogmaneo-b200: wrong number of input CSDRs");
+    if (devIn && devIn->size() != (size_t)NI) throw std::invalid_argument("ogmaneo-b200: wrong number of input CSDRs");
 
     ctx.beginStep();
     ticks[0] = 0;
@@ -182,8 +182,7 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const std::vector<const IntBuffer *>
         r.pushFront();
         consumeKernel1(cs, (int)(r.n / m.batch));
         if (hostIn) {
-            if ((*hostIn)[i]->size() != r.n) throw std::invalid_argument("ogmaneo-b200: input CSDR has the wrong number of columns");
-            std::memcpy(m.inPinned[i]->ptr(), (*hostIn)[i]->data(), r.n * sizeof(int));
+            std::memcpy(m.inPinned[i]->ptr(), hostIn[i], r.n * sizeof(int));
             cudaCheck(cudaMemcpyAsync(r.slot(0), m.inPinned[i]->ptr(), r.n * sizeof(int), cudaMemcpyHostToDevice, ctx.stream), "input H2D");
         } else
             cudaCheck(cudaMemcpyAsync(r.slot(0), (*devIn)[i], r.n * sizeof(int), cudaMemcpyDeviceToDevice, ctx.stream), "input D2D");
@@ -254,7 +253,26 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const std::vector<const IntBuffer *>
 }
 
 void Hierarchy::step(ComputeSystem &cs, const std::vector<const IntBuffer *> &inputCs, bool learnEnabled, float reward, bool mimic) {
-    stepImpl(cs, &inputCs, nullptr, learnEnabled, reward, mimic);
+    if (inputCs.size() != inputSizes.size()) throw std::invalid_argument("ogmaneo-b200: wrong number of input CSDRs");
+    std::vector<const int *> raw(inputCs.size());
+    for (size_t i = 0; i < inputCs.size(); i++) {
+        if (inputCs[i]->size() != impl->histories[0][i].n) throw std::invalid_argument("ogmaneo-b200: input CSDR has the wrong number of columns");
+        raw[i] = inputCs[i]->data();
+    }
+    stepImpl(cs, raw.data(), nullptr, learnEnabled, reward, mimic);
+}
+
+void Hierarchy::stepHost(ComputeSystem &cs, const int *const *inputCs, bool learnEnabled, float reward, bool mimic) {
+    stepImpl(cs, inputCs, nullptr, learnEnabled, reward, mimic);
+}
+
+int Hierarchy::copyPredictionCs(int i, int *out) const {
+    if (aLayers[i] != nullptr) {
+        const IntBuffer &b = aLayers[i]->getHiddenCs();
+        std::memcpy(out, b.data(), b.size() * sizeof(int));
+        return (int)b.size();
+    }
+    return pLayers.front()[i]->copyHiddenCs(out);
 }
 
 void Hierarchy::stepDevice(ComputeSystem &cs, const std::vector<const int *> &inputCsDevice, bool learnEnabled, float reward, bool mimic) {

@@ -44,6 +44,7 @@ struct Predictor::Impl {
     int prevCur = 0;
     std::vector<detail::DevBuf<int>> inStage;
     detail::DevBuf<int> targetStage;
+    detail::PinnedBuf<int> csPinned; // staging of hiddenCs downloads (pageable destinations are several times slower)
     bool csDirty = true, actDirty = true, prevDirty = true;
     std::vector<char> wDirty;
 

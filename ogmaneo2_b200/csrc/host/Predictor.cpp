@@ -134,17 +134,35 @@ void Predictor::learn(ComputeSystem &cs, const IntBuffer *hiddenTargetCs) {
 }
 
 // --- host mirrors ------------------------------------------------------------------------------------------------
+namespace {
+// device hiddenCs -> pinned staging, waits; returns the staging pointer
+const int *stageHiddenCs(Predictor::Impl &m) {
+    cudaCheck(cudaSetDevice(m.ctx->device), "cudaSetDevice");
+    m.ctx->joinExchange(); // a deferred exchange of this CSDR may still be running on the side stream
+    if (m.csPinned.size() != m.hiddenCs.size()) m.csPinned.alloc(m.hiddenCs.size());
+    m.hiddenCs.download(m.csPinned.ptr(), m.hiddenCs.size(), m.ctx->stream);
+    cudaCheck(cudaStreamSynchronize(m.ctx->stream), "cudaStreamSynchronize");
+    m.ctx->peerCheck();
+    return m.csPinned.ptr();
+}
+} // namespace
+
 const IntBuffer &Predictor::getHiddenCs() const {
     Impl &m = *impl;
     if (m.csDirty) {
-        cudaCheck(cudaSetDevice(m.ctx->device), "cudaSetDevice");
-        m.ctx->joinExchange(); // a deferred exchange of this CSDR may still be running on the side stream
-        hiddenCs.resize(m.hiddenCs.size());
-        m.hiddenCs.download(hiddenCs.data(), hiddenCs.size(), m.ctx->stream);
-        m.ctx->sync();
+        const int *p = stageHiddenCs(m);
+        hiddenCs.assign(p, p + m.hiddenCs.size());
         m.csDirty = false;
     }
     return hiddenCs;
+}
+
+int Predictor::copyHiddenCs(int *out) const {
+    Impl &m = *impl;
+    const size_t n = m.hiddenCs.size();
+    if (!m.csDirty) std::memcpy(out, hiddenCs.data(), n * sizeof(int));
+    else std::memcpy(out, stageHiddenCs(m), n * sizeof(int));
+    return (int)n;
 }
 
 const FloatBuffer &Predictor::getHiddenActivations() const {
