@@ -67,6 +67,12 @@ def workload(name, n_gpus, size=None):
         cfg["desc"] = "C3: 8x8x16 observation + 2x2x4 action -> 3 layers 8x8x16, Actor head"
         cfg["sample"] = configs.c3_actor(8)
         cfg["device_init"] = False
+    elif name == "c5":
+        cfg = configs.c5_unit(16)
+        cfg["desc"] = ("C5: ensemble of independent hierarchies stepped in lockstep, each 16x16x16 input -> 4 layers 16x16x16, r=2 "
+                       "(member k: seed 1234+k, stream shifted by 17k)")
+        cfg["sample"] = configs.c5_unit(16)
+        cfg["device_init"] = True
     else:
         raise SystemExit(f"unknown workload {name}")
     cfg["key"] = name
@@ -220,6 +226,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: CSDR slab exchange by the library's peer-memory kernel (default) or NCCL all-gather")
+    ap.add_argument("--ensemble", type=int, default=512, help="c5 only: hierarchies per GPU (weak scaling; 512 = 80 GB)")
     ap.add_argument("--size", type=int, default=None, help="c4 only: grid edge (default 512); smaller sizes are for profiling runs")
     args = ap.parse_args()
 
@@ -247,8 +254,8 @@ def main():
 
     # ------------------------------------------------------------------------------------------------ B200 arm
     # defaults: the step counts SURVEY.md §8d prescribes for each config (C4: 200 warm-up + 300 timed)
-    K = args.steps if args.steps is not None else (300 if args.workload == "c4" else 2000)
-    W = args.warmup if args.warmup is not None else (200 if args.workload == "c4" else 300)
+    K = args.steps if args.steps is not None else {"c4": 300, "c5": 200}.get(args.workload, 2000)
+    W = args.warmup if args.warmup is not None else {"c4": 200, "c5": 50}.get(args.workload, 300)
     W = max(W, 3)
     import torch
     import ogmaneo2_b200 as og
@@ -265,11 +272,17 @@ def main():
     if args.gpus != world:
         raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run")
 
-    peer = world > 1 and args.exchange == "peer"
-    opt = og.CreateOptions(device=local_rank, deviceInit=cfg["device_init"], replayRng=False, shardRank=rank, shardWorld=world,
-                           peerExchange=peer)
+    ens = args.workload == "c5"
+    B = args.ensemble if ens else 1
+    peer = world > 1 and args.exchange == "peer" and not ens
+    if ens:  # members shard across GPUs with no exchange at all: rank r steps members [r*B, (r+1)*B)
+        opt = og.CreateOptions(device=local_rank, deviceInit=True, replayRng=False,
+                               ensembleSeeds=[1234 + rank * B + k for k in range(B)])
+    else:
+        opt = og.CreateOptions(device=local_rank, deviceInit=cfg["device_init"], replayRng=False, shardRank=rank, shardWorld=world,
+                               peerExchange=peer)
     ext = {}
-    if world > 1 and not peer:
+    if world > 1 and not peer and not ens:
         cache = {}
 
         def all_gather(buf, count, stream_ptr):
@@ -295,7 +308,13 @@ def main():
     has_action = "action" in kinds
     n_in = len(cfg["inputSizes"])
     total = W + K
-    host_in = [np.stack([streams.make(k if k != "action" else "iid", t, s) for t in range(total)]) for s, k in zip(cfg["inputSizes"], kinds)]
+    if ens:
+        gk = [rank * B + k for k in range(B)]
+        host_in = [np.stack([np.concatenate([streams.make(kinds[0], t, cfg["inputSizes"][0], seed=7 + k, shift=17 * k) for k in gk])
+                             for t in range(total)])]
+    else:
+        host_in = [np.stack([streams.make(k if k != "action" else "iid", t, s) for t in range(total)])
+                   for s, k in zip(cfg["inputSizes"], kinds)]
     dev_in = [torch.from_numpy(a).to(f"cuda:{local_rank}") for a in host_in]
     torch.cuda.synchronize()
 
@@ -340,7 +359,7 @@ def main():
         ms = float(t.item())
         ranks_info = [None] * world
         dist.all_gather_object(ranks_info, mine)
-    value = K / (ms / 1000.0)
+    value = K / (ms / 1000.0) * (B * world if ens else 1)  # c5: hierarchy steps/s summed over every member on every GPU
 
     # ------------------------------------------------------------------------------------------------ e2e (host API)
     Ke = K
@@ -358,7 +377,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     h2d = sum(int(a[0].nbytes) for a in host_in)
-    d2h = sum(cfg["inputSizes"][i][0] * cfg["inputSizes"][i][1] * 4 for i in pred_idx)
+    d2h = sum(cfg["inputSizes"][i][0] * cfg["inputSizes"][i][1] * 4 * B for i in pred_idx)
 
     if rank != 0:
         if dist is not None:
@@ -378,7 +397,8 @@ def main():
     alg = {}
     for (l, kind, b, per_pair) in sites:
         a = alg.setdefault(kind, 0.0)
-        alg[kind] = a + b * counts[l] / max(world, 1)  # bytes one rank moves (x-slab sharding splits every launch)
+        # bytes one rank moves: x-slab sharding splits every launch; an ensemble multiplies it by the members per GPU
+        alg[kind] = a + (b * counts[l] * B if ens else b * counts[l] / max(world, 1))
     # data-dependent SC writes (4 B x Vz per rewritten pair): the update kernel's bytes when learn ran as two kernels
     upd_bytes = sum(u * 4 * cfg["inputSizes"][0][2] if l == 0 else u * 4 * cfg["layerDescs"][l - 1].hiddenSize[2]
                     for l, u in enumerate(upd))
@@ -412,19 +432,21 @@ def main():
         except Exception as e:  # the baseline must never take the GPU result down with it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
 
-    config.update({"parallelism": (f"x-slab sharding over {world} GPUs, CSDR slabs exchanged by "
-                                   f"{'a peer-memory (NVLink) all-gather kernel' if peer else 'NCCL all-gather'}")
-                   if world > 1 else "single GPU",
-                   "l2": "per-step weight traffic (GBs) far exceeds the 126 MB L2; no flush needed" if args.workload == "c4"
+    config.update({"parallelism": (f"{B} ensemble members per GPU x {world} GPU(s), no exchange" if ens else
+                                   (f"x-slab sharding over {world} GPUs, CSDR slabs exchanged by "
+                                    f"{'a peer-memory (NVLink) all-gather kernel' if peer else 'NCCL all-gather'}")
+                                   if world > 1 else "single GPU"),
+                   "l2": "per-step weight traffic (GBs) far exceeds the 126 MB L2; no flush needed" if args.workload in ("c4", "c5")
                    else "weights exceed L2" if args.workload == "c2" else "L2-resident (latency-bound config)",
                    "init": "device counter-hash" if cfg["device_init"] else "std::mt19937 in reference order",
                    "kernel_timing": f"CUDA events around every kernel launch of every {PROF_PERIOD}th step of the timed region"})
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "higher_is_better": True, "scaling": "weak" if ens else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": config, "roofline": roofline, "cpu_baseline": cpu,
-           "e2e": {"value": Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+           "e2e": {"value": Ke / e2e_s * (B * world if ens else 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
            "gpu_launches": int(sum(n for _, n in prof.values())), "clocks": clk,
-           "ranks": ranks_info, "column_steps_per_s": value * sum(ld.hiddenSize[0] * ld.hiddenSize[1] * c for ld, c in zip(cfg["layerDescs"], counts)) / K}
+           "ranks": ranks_info,
+           "column_steps_per_s": value * sum(ld.hiddenSize[0] * ld.hiddenSize[1] * c for ld, c in zip(cfg["layerDescs"], counts)) / K}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -81,6 +81,7 @@ public:
     // without building IntBuffers first
     void stepHost(ComputeSystem &cs, const int *const *inputCs, bool learnEnabled = true, float reward = 0.0f, bool mimic = false);
     // getPredictionCs(i) copied straight into out (pinned staging, no host mirror refresh); returns the column count
+    // (out == nullptr: only the count)
     int copyPredictionCs(int i, int *out) const;
     // Same as step() but the inputs are already in device memory (int32, [member][columns] each) and nothing is copied
     // back: the whole step is asynchronous on cs' stream.

@@ -269,7 +269,7 @@ void Hierarchy::stepHost(ComputeSystem &cs, const int *const *inputCs, bool lear
 int Hierarchy::copyPredictionCs(int i, int *out) const {
     if (aLayers[i] != nullptr) {
         const IntBuffer &b = aLayers[i]->getHiddenCs();
-        std::memcpy(out, b.data(), b.size() * sizeof(int));
+        if (out) std::memcpy(out, b.data(), b.size() * sizeof(int));
         return (int)b.size();
     }
     return pLayers.front()[i]->copyHiddenCs(out);

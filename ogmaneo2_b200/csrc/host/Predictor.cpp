@@ -160,6 +160,7 @@ const IntBuffer &Predictor::getHiddenCs() const {
 int Predictor::copyHiddenCs(int *out) const {
     Impl &m = *impl;
     const size_t n = m.hiddenCs.size();
+    if (!out) return (int)n; // size query
     if (!m.csDirty) std::memcpy(out, hiddenCs.data(), n * sizeof(int));
     else std::memcpy(out, stageHiddenCs(m), n * sizeof(int));
     return (int)n;
