@@ -38,7 +38,7 @@ from ogmaneo2_b200.flat_api import FlatHierarchy, InputType  # noqa: E402
 METRIC = "hierarchy_steps_per_s_learn_on"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel at the default workload (C4 512x512), from the
 # `ncu --set full` capture summarised in profiles/README.md (filled in from the capture; None = not captured)
-TRAFFIC = {}
+TRAFFIC = {"sc_forward": 2.6998e9, "sc_learn": 1.5106e9, "pred_step": 4.3558e9, "sc_update": 1.9418e9}  # sc_update: at U = 1.3 M pairs
 PROF_PERIOD = 8
 UNIT = "steps/s"
 
@@ -50,7 +50,7 @@ def workload(name, n_gpus, size=None):
         n = size or 512
         cfg = configs.c4_large(n)
         cfg["desc"] = f"C4: {n}x{n}x16 input CSDR -> 1 layer {n}x{n}x32 hidden columns, r=4, temporalHorizon=1, noisy(2%) stream"
-        cfg["sample"] = configs.c4_large(64)
+        cfg["sample"] = configs.c4_large(128)  # SURVEY.md's oracle size for this config: ~20 s of reference init + ~10 s of steps
         cfg["device_init"] = True  # 2.2e10 weights: the reference cannot even construct this size
     elif name == "c2":
         cfg = configs.c2_video(32, 3)
@@ -243,7 +243,7 @@ def main():
             return
         K = args.steps if args.steps is not None else 10
         W = args.warmup if args.warmup is not None else 3
-        value, info = time_cpu(cfg["sample"], K, W, full_cols, budget_s=120.0)
+        value, info = time_cpu(cfg["sample"], max(K, 40) if args.workload == "c4" else K, W, full_cols, budget_s=60.0)
         info["value"] = value
         info["unit"] = UNIT
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
@@ -418,7 +418,10 @@ def main():
     dom = max(cand, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches"]) if cand else None
     total_alg = sum(alg.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["achieved_gbs"] / peak if dom else None, "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
+                "frac": kernels[dom]["achieved_gbs"] / peak if dom else None,
+                "traffic": TRAFFIC.get(dom) if args.workload == "c4" and world == 1 and not args.size else None,
+                "traffic_source": "profiles/r1_ncu_c4_512_summary.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                "peak_source": peak_src,
                 "step_achieved_gbs": total_alg / (ms * 1e-3) / 1e9, "step_frac": total_alg / (ms * 1e-3) / 1e9 / peak,
                 "alg_bytes_per_step_per_gpu": total_alg / K, "kernels": kernels,
                 "sc_pairs_rewritten_per_step": [u / K for u in upd]}
@@ -426,7 +429,7 @@ def main():
     cpu = None
     if not args.no_cpu and args.gpus == 1:
         try:
-            v, info = time_cpu(cfg["sample"], 10, 1, full_cols, budget_s=20.0)
+            v, info = time_cpu(cfg["sample"], 60 if args.workload == "c4" else 10, 1, full_cols, budget_s=12.0)
             info["value"], info["unit"] = v, UNIT
             cpu = info
         except Exception as e:  # the baseline must never take the GPU result down with it
