@@ -224,6 +224,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--stream", default="noisy", help="input stream kind for prediction inputs: noisy|coherent|iid")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--burnin", type=int, default=None,
+                    help="c4: untimed training steps BEFORE the W warm-up steps so that the hierarchy is always measured in the "
+                         "regime SURVEY.md §8d prescribes (200 steps of learning on the stream before the timed region); "
+                         "default max(0, 200 - W)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: CSDR slab exchange by the library's peer-memory kernel (default) or NCCL all-gather")
     ap.add_argument("--ensemble", type=int, default=512, help="c5 only: hierarchies per GPU (weak scaling; 512 = 80 GB)")
@@ -257,6 +261,7 @@ def main():
     K = args.steps if args.steps is not None else {"c4": 300, "c5": 200}.get(args.workload, 2000)
     W = args.warmup if args.warmup is not None else {"c4": 200, "c5": 50}.get(args.workload, 300)
     W = max(W, 3)
+    burn = args.burnin if args.burnin is not None else (max(0, 200 - W) if args.workload == "c4" else 0)
     import torch
     import ogmaneo2_b200 as og
     from ogmaneo2_b200 import build
@@ -307,7 +312,7 @@ def main():
     kinds = [args.stream if k in ("noisy", "coherent", "iid") else k for k in cfg["streams"]]
     has_action = "action" in kinds
     n_in = len(cfg["inputSizes"])
-    total = W + K
+    total = burn + W + K
     if ens:
         gk = [rank * B + k for k in range(B)]
         host_in = [np.stack([np.concatenate([streams.make(kinds[0], t, cfg["inputSizes"][0], seed=7 + k, shift=17 * k) for k in gk])
@@ -327,7 +332,8 @@ def main():
         for t in range(t0, t0 + n):
             h.stepDevice([d[t].data_ptr() for d in dev_in], True)
 
-    run_device(0, W)
+    run_device(0, burn)  # state preparation (the data-dependent SparseCoder write rate falls from 30 % to 3 % of the pairs)
+    run_device(burn, W)
     barrier()
     for l in range(len(cfg["layerDescs"])):
         h.takeSCUpdateCount(l)
@@ -341,7 +347,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
     e0.record(ext["s"])
-    run_device(W, K)
+    hq0 = time.perf_counter()
+    run_device(burn + W, K)
+    host_enqueue_ms = (time.perf_counter() - hq0) * 1e3 / K  # host time to queue one step (no waiting unless a queue fills up)
     e1.record(ext["s"])
     barrier()
     wall1 = time.time()
@@ -355,6 +363,8 @@ def main():
         t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         mine = {"step_ms": ms / K, "kernel_ms_per_step": sum(v[0] for v in prof.values()) / K,
+                "sc_pairs_rewritten_per_step": sum(upd) / K, "host_enqueue_ms_per_step": host_enqueue_ms,
+                "kernel_ms": {k: round(v[0] / K, 4) for k, v in prof.items() if v[1]},
                 "exchange_wait_us_per_step": (h.peerTakeWaitNs() / 1e3 / K) if peer else None}
         ms = float(t.item())
         ranks_info = [None] * world
@@ -366,7 +376,7 @@ def main():
     barrier()
     pred_idx = [i for i, t in enumerate(cfg["inputTypes"]) if t != InputType.none]
     w0 = time.perf_counter()
-    for t in range(W, W + Ke):
+    for t in range(burn + W, burn + W + Ke):
         h.step([a[t] for a in host_in], True)
         for i in pred_idx:
             h.getPredictionCs(i)
@@ -393,7 +403,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     sites = bytes_per_launch(cfg)
-    counts = tick_counts(cfg, W + K)[W:].sum(axis=0)  # updates per layer inside the timed region
+    counts = tick_counts(cfg, burn + W + K)[burn + W:].sum(axis=0)  # updates per layer inside the timed region
     alg = {}
     for (l, kind, b, per_pair) in sites:
         a = alg.setdefault(kind, 0.0)
@@ -442,13 +452,14 @@ def main():
                    "l2": "per-step weight traffic (GBs) far exceeds the 126 MB L2; no flush needed" if args.workload in ("c4", "c5")
                    else "weights exceed L2" if args.workload == "c2" else "L2-resident (latency-bound config)",
                    "init": "device counter-hash" if cfg["device_init"] else "std::mt19937 in reference order",
+                   "burn_in_steps": burn,
                    "kernel_timing": f"CUDA events around every kernel launch of every {PROF_PERIOD}th step of the timed region"})
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
            "higher_is_better": True, "scaling": "weak" if ens else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": config, "roofline": roofline, "cpu_baseline": cpu,
            "e2e": {"value": Ke / e2e_s * (B * world if ens else 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
            "gpu_launches": int(sum(n for _, n in prof.values())), "clocks": clk,
-           "ranks": ranks_info,
+           "ranks": ranks_info, "host_enqueue_ms_per_step": host_enqueue_ms,
            "column_steps_per_s": value * sum(ld.hiddenSize[0] * ld.hiddenSize[1] * c for ld, c in zip(cfg["layerDescs"], counts)) / K}
     print(json.dumps(out))
     if dist is not None:

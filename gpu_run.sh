@@ -1,15 +1,12 @@
 cd /root/repo
 mkdir -p gpurun_out/final
 O=gpurun_out/final
-nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $O/gpu.txt
-( time python -m pytest tests -m gpu -x -q ) > $O/tests_gpu.log 2>&1; tail -4 $O/tests_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
-( time python bench.py ) > $O/bench_n1.log 2>&1; tail -1 $O/bench_n1.log | cut -c1-400
-( time python bench.py --impl reference --steps 10 --warmup 3 ) > $O/bench_ref.log 2>&1; tail -4 $O/bench_ref.log | cut -c1-300
-python bench.py --steps 20 --warmup 3 --no-cpu > $O/plain_launch.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_c4_512.csv python bench.py --steps 20 --warmup 3 --no-cpu > $O/ncu_launch.log 2>&1
-tail -2 $O/launches_c4_512.csv | cut -c1-200
-python bench.py --steps 12 --warmup 100 --no-cpu > $O/plain_full.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'k_(sc|pred)' -s 400 -c 4 -o $O/prof_r1_c4_512 python bench.py --steps 12 --warmup 100 --no-cpu > $O/ncu_full.log 2>&1
-tail -3 $O/ncu_full.log | cut -c1-200
-ls -la $O
+N=${NGPU:-8}
+nproc > $O/nproc.txt; lscpu | head -20 >> $O/nproc.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 150 --warmup 50 --burnin 0 > $O/bench_n${N}c.log 2>&1
+grep -a '^{' $O/bench_n${N}c.log | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('N=%d steps/s %.1f ms/step %.3f e2e %.1f step_frac %.3f'%(d['n_gpus'],d['value'],d['ms_per_step'],d['e2e']['value'],r['step_frac']))
+for i,x in enumerate(d.get('ranks') or []): print('   rank',i,'host_enqueue %.3f wait_us %.1f kernel_ms %s'%(x['host_enqueue_ms_per_step'],x['exchange_wait_us_per_step'],x['kernel_ms']))"
+cat $O/nproc.txt | head -12
