@@ -48,6 +48,7 @@ public:
     const FloatBuffer &getHiddenActivations() const; // private in the reference (Predictor.h:42)
     void getWeights(int i, std::vector<float> &out) const;
     const IntBuffer &getInputCsPrev(int i) const;
+    void stateSignature(std::vector<int> &key) const; // everything that selects this layer's kernel arguments (graph cache key)
     int copyHiddenCs(int *out) const; // getHiddenCs() straight into out (pinned staging); returns the column count
     void initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize, const std::vector<VisibleLayerDesc> &visibleLayerDescs,
                           int batch, int member);

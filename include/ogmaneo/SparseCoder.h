@@ -61,6 +61,7 @@ public:
                           int batch, int member);
     // step() on inputs that already live in device memory (int32 [member][columns]); copyOut (optional) also receives
     // the new hiddenCs. Asynchronous on cs' stream.
+    void stateSignature(std::vector<int> &key) const; // everything that selects this layer's kernel arguments (graph cache key)
     void stepDevice(ComputeSystem &cs, const int *const *inputCsDevice, bool learnEnabled, int *copyOut);
     const int *hiddenCsDevice() const;
     void readFromStream(std::istream &is, ComputeSystem &cs); // choose the device / stream to load onto

@@ -36,6 +36,7 @@ DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
     cudaCheck(cudaEventCreateWithFlags(&evExchange, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evPredLearn, cudaEventDisableTiming), "cudaEventCreate");
     if (const char *e = std::getenv("OGN_SIDE_STREAM")) useSide = std::atoi(e) != 0; // 0: everything on one stream
+    if (const char *e = std::getenv("OGN_GRAPHS")) graphs = std::atoi(e) != 0;
 }
 
 void DeviceContext::forkSide() {

@@ -64,6 +64,9 @@ struct DeviceContext {
     cudaStream_t side;
     cudaEvent_t evFork, evLearn, evExchange, evPredLearn;
     bool learnPending = false, exchangePending = false, useSide = true;
+    // graphs: Hierarchy::step may capture its kernel sequence into CUDA graphs (OGN_GRAPHS=0 disables). dry: the step's
+    // host code runs for its state transitions only, nothing is queued (the captured graph is launched instead).
+    bool graphs = true, dry = false;
     void forkSide();
     void learnQueued();     // call after queueing learn work on `side`
     void exchangeQueued();  // call after queueing a deferred exchange on `side`

@@ -3,6 +3,7 @@
 #include "LayerImpl.h"
 
 #include <cassert>
+#include <map>
 
 namespace ogmaneo {
 using namespace detail;
@@ -20,13 +21,30 @@ struct Ring {
 };
 } // namespace
 
+// One captured step: the kernels Hierarchy::step queues are a pure function of the tick pattern, the ring positions and
+// the ping-pong parities, so each distinct combination is captured once (cudaStreamBeginCapture) and replayed with a
+// single cudaGraphLaunch afterwards. Small hierarchies are otherwise bound by the host's launch calls (8-16 per step).
+struct StepGraph {
+    int seen = 0;
+    cudaGraphExec_t exec = nullptr;
+};
+
 struct Hierarchy::Impl {
     std::shared_ptr<DeviceContext> ctx;
     int batch = 1;
+    std::map<std::vector<int>, StepGraph> graphs;
+    void dropGraphs() {
+        for (auto &g : graphs)
+            if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+        graphs.clear();
+    }
     std::vector<std::vector<Ring>> histories; // [layer][input]
     std::vector<std::unique_ptr<PinnedBuf<int>>> inPinned;
     cudaEvent_t inFree = nullptr; // pinned input staging may be overwritten after this event
-    ~Impl() { if (inFree) cudaEventDestroy(inFree); }
+    ~Impl() {
+        dropGraphs();
+        if (inFree) cudaEventDestroy(inFree);
+    }
 };
 
 Hierarchy::Hierarchy() : impl(nullptr) {}
@@ -189,6 +207,7 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
     }
     if (hostIn) cudaCheck(cudaEventRecord(m.inFree, ctx.stream), "cudaEventRecord");
 
+    auto body = [&]() {
     // Sharded layers: the learn pass of the layer-0 Predictors needs nothing this step produces (its target is the
     // input just copied, its gather rows are last step's inputs), so it is hoisted to the side stream and runs while the
     // main stream does the SparseCoder forward pass and its slab exchange; the activate pass follows on the main stream.
@@ -250,6 +269,42 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
     // SparseCoder learn ran on the side stream, concurrently with the Predictors above: everything queued on the main
     // stream from here on (the next step, getters, copies) is ordered behind it
     ctx.joinLearn();
+    };
+
+    // Graph replay (single device, single stream, no Actor: the Actor uploads fresh host-drawn numbers every step; a
+    // profiled step is queued normally so that its kernels can be bracketed by events).
+    bool graphOk = ctx.graphs && !ctx.useSide && cs.shardWorld == 1 && !(ctx.profiling && ctx.sampleThis) && m.graphs.size() < 1024;
+    for (size_t p = 0; p < aLayers.size() && graphOk; p++)
+        if (aLayers[p]) graphOk = false;
+    if (!graphOk) { body(); return; }
+    std::vector<int> key;
+    key.push_back(learnEnabled ? 1 : 0);
+    key.insert(key.end(), ticks.begin(), ticks.end());
+    for (int l = 0; l < L; l++) {
+        scLayers[l].stateSignature(key);
+        for (auto &r : m.histories[l]) key.push_back(r.start);
+        for (auto &pl : pLayers[l])
+            if (pl) pl->stateSignature(key);
+    }
+    StepGraph &g = m.graphs[key];
+    if (g.exec) { // host-side state transitions only, then one launch
+        ctx.dry = true;
+        try { body(); } catch (...) { ctx.dry = false; throw; }
+        ctx.dry = false;
+        cudaCheck(cudaGraphLaunch(g.exec, ctx.stream), "cudaGraphLaunch");
+    } else if (g.seen >= 1) { // second occurrence: every lazy initialisation behind it, capture
+        cudaCheck(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+        cudaGraph_t graph = nullptr;
+        try { body(); } catch (...) { cudaStreamEndCapture(ctx.stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        cudaCheck(cudaStreamEndCapture(ctx.stream, &graph), "cudaStreamEndCapture");
+        cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        cudaCheck(e, "cudaGraphInstantiate");
+        cudaCheck(cudaGraphLaunch(g.exec, ctx.stream), "cudaGraphLaunch");
+    } else {
+        g.seen++;
+        body();
+    }
 }
 
 void Hierarchy::step(ComputeSystem &cs, const std::vector<const IntBuffer *> &inputCs, bool learnEnabled, float reward, bool mimic) {

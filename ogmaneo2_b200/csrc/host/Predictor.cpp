@@ -97,7 +97,7 @@ void Predictor::stepDevice(ComputeSystem &cs, bool learn, const int *targetDev, 
     // onSideStream: a learn-only pass the caller hoisted to the side stream (see Hierarchy::step)
     cudaStream_t st = (onSideStream && ctx.useSide && !activate) ? ctx.side : ctx.stream;
     { LaunchScope ls(ctx, kPredStep, st);
-    kernelCheck(ogn_pred_step(&a, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, learn ? 1 : 0, activate ? 1 : 0,
+    if (!ctx.dry) kernelCheck(ogn_pred_step(&a, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, learn ? 1 : 0, activate ? 1 : 0,
                               targetDev, alpha, m.acts.ptr(), m.hiddenCs.ptr(), st), "pred_step"); }
     if (learn) std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
     if (activate) {
@@ -277,5 +277,12 @@ void Predictor::setState(const IntBuffer &hc, const std::vector<IntBuffer> &prev
 }
 
 const int *Predictor::hiddenCsDevice() const { return impl->hiddenCs.ptr(); }
+
+void Predictor::stateSignature(std::vector<int> &key) const {
+    key.push_back(impl->prevCur);
+    int a;
+    std::memcpy(&a, &alpha, sizeof(a));
+    key.push_back(a);
+}
 
 } // namespace ogmaneo

@@ -103,7 +103,7 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
 
     consumeKernel2(cs, hiddenSize.x, hiddenSize.y);
     { LaunchScope ls(ctx, kScForward);
-    kernelCheck(ogn_sc_forward(&fa, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, out, sharded ? nullptr : copyOut,
+    if (!ctx.dry) kernelCheck(ogn_sc_forward(&fa, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, out, sharded ? nullptr : copyOut,
                                ctx.stream), "sc_forward"); }
     if (sharded) {
         if (ctx.arena && ctx.inArena(out)) ctx.peerAllGather(out, (m.x1 - m.x0) * hiddenSize.y);
@@ -137,11 +137,11 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
             }
             // reconstruction (or the whole fused learn when the 128-bit path does not apply), then the work-list update
             { LaunchScope ls(ctx, kScLearn, lst);
-            kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_RECONSTRUCT, lst),
+            if (!ctx.dry) kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_RECONSTRUCT, lst),
                         "sc_learn"); }
             if (ogn_sc_learn_is_split(&la)) {
                 LaunchScope ls(ctx, kScUpdate, lst);
-                kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_UPDATE, lst),
+                if (!ctx.dry) kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_UPDATE, lst),
                             "sc_update");
             }
             v = e;
@@ -314,5 +314,12 @@ void SparseCoder::setHiddenState(const IntBuffer &hc, const IntBuffer &hcPrev) {
 }
 
 const int *SparseCoder::hiddenCsDevice() const { return impl->cs_[impl->cur].ptr(); }
+
+void SparseCoder::stateSignature(std::vector<int> &key) const {
+    key.push_back(impl->cur); key.push_back(impl->prevAliasesCur ? 1 : 0);
+    int a;
+    std::memcpy(&a, &alpha, sizeof(a));
+    key.push_back(a);
+}
 
 } // namespace ogmaneo
