@@ -128,6 +128,19 @@ typedef struct ogn_wset {
     int fx0, fx1, rx0, rx1;
 } ogn_wset;
 
+/* History samples of one Actor::learn launch (Actor.cpp:280-309: historyIters samples per step, applied in order). */
+#define OGN_MAX_ACTOR_SAMPLES 16
+typedef struct ogn_actor_sample {
+    const int *cs[OGN_MAX_PRED_VL]; /* sPrev.inputCs of every visible layer */
+    const int *target_prev;         /* s.hiddenTargetCsPrev */
+    const float *values_prev;       /* sPrev.hiddenValues */
+    float q, g;                     /* discounted reward sum and gamma^(index+1) */
+} ogn_actor_sample;
+typedef struct ogn_actor_batch {
+    ogn_actor_sample it[OGN_MAX_ACTOR_SAMPLES];
+    int n;
+} ogn_actor_batch;
+
 const char *ogn_cuda_error_string(int code);
 
 /* K2 — SparseCoder::forward (SparseCoder.cpp:13-43) + multiplyOHVs (SparseMatrix.cpp:260-276) over hidden x in
@@ -163,10 +176,11 @@ int ogn_pred_step(const ogn_pred_args *args_host, int Hx, int Hy, int Hz, int x0
 int ogn_actor_forward(const ogn_actor_args *args_host, int Hx, int Hy, int Hz, const float *u01, float *hidden_values,
                       float *hidden_activations, int *hidden_cs, void *stream);
 
-/* K11 — Actor::learn (Actor.cpp:92-185) on one history pair. args.vl[v].cs = sPrev.inputCs[v]. */
-int ogn_actor_learn(const ogn_actor_args *args_host, int Hx, int Hy, int Hz, const int *target_cs_prev,
-                    const float *hidden_values_prev, const float *hidden_values, float q, float g, float alpha, float beta,
-                    int mimic, float *hidden_activations, void *stream);
+/* K11 — Actor::learn (Actor.cpp:92-185) on batch->n history pairs, applied one after the other inside one launch (each
+ * action column owns its weights, so the per-sample launches of the reference collapse without changing the result).
+ * args.vl[v].cs is ignored; the samples carry the CSDR pointers. */
+int ogn_actor_learn(const ogn_actor_args *args_host, const ogn_actor_batch *batch_host, int Hx, int Hy, int Hz,
+                    const float *hidden_values, float alpha, float beta, int mimic, float *hidden_activations, void *stream);
 
 /* Peer-memory all-gather of a sharded CSDR (multi-GPU, one process per GPU): base[r] is rank r's exchange arena as mapped
  * in THIS process (CUDA IPC); the buffer lives at the same offset in every arena. One launch: this rank's slab

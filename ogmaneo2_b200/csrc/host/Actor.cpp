@@ -29,7 +29,10 @@ Actor &Actor::operator=(const Actor &o) {
         for (size_t v = 0; v < s.histInput.size(); v++) impl->histInput[v].cloneFrom(s.histInput[v], ctx.stream);
         impl->histTarget.cloneFrom(s.histTarget, ctx.stream); impl->histValues.cloneFrom(s.histValues, ctx.stream);
         impl->inStage.resize(s.inStage.size());
-        cudaCheck(cudaEventCreateWithFlags(&impl->u01Free, cudaEventDisableTiming), "cudaEventCreate");
+        for (auto &e : impl->u01Free) {
+            cudaCheck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+            cudaCheck(cudaEventRecord(e, ctx.stream), "cudaEventRecord");
+        }
         ctx.sync();
     }
     return *this;
@@ -47,7 +50,7 @@ void Actor::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, int historyCap
     acts.allocZero((size_t)ncols * hidden.z, ctx->stream);
     values.allocZero(ncols, ctx->stream);
     hiddenCs.allocZero(ncols, ctx->stream);
-    u01.allocZero(ncols, ctx->stream); u01Host.alloc(ncols);
+    u01.allocZero(ncols, ctx->stream); u01Host.alloc((size_t)ncols * kU01Slots);
     capacity = historyCapacity; start = 0; historySize = 0;
     histInput.clear(); histInput.resize(vlds.size());
     for (size_t v = 0; v < vlds.size(); v++) histInput[v].allocZero((size_t)capacity * vlds[v].size.x * vlds[v].size.y, ctx->stream);
@@ -55,8 +58,10 @@ void Actor::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, int historyCap
     histValues.allocZero((size_t)capacity * ncols, ctx->stream);
     rewards.assign(capacity, 0.0f);
     inStage.clear(); inStage.resize(vlds.size());
-    if (!u01Free) cudaCheck(cudaEventCreateWithFlags(&u01Free, cudaEventDisableTiming), "cudaEventCreate");
-    cudaCheck(cudaEventRecord(u01Free, ctx->stream), "cudaEventRecord");
+    for (auto &e : u01Free) {
+        if (!e) cudaCheck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+        cudaCheck(cudaEventRecord(e, ctx->stream), "cudaEventRecord");
+    }
     csDirty = valDirty = true; wDirty.assign(vlds.size(), 1);
 }
 
@@ -85,17 +90,20 @@ void Actor::stepDevice(ComputeSystem &cs, const int *const *inputDev, const int 
     // by = i / nbx, columns visited x-outer / y-inner, one canonical float each (Helpers.cpp:46-70, Actor.cpp:70-72).
     std::vector<int> seeds;
     consumeKernel2(cs, Hx, Hy, &seeds);
-    cudaCheck(cudaEventSynchronize(m.u01Free), "cudaEventSynchronize");
+    const int us = m.u01Slot;
+    m.u01Slot = (m.u01Slot + 1) % Impl::kU01Slots;
+    float *u01h = m.u01Host.ptr() + (size_t)us * ncols;
+    cudaCheck(cudaEventSynchronize(m.u01Free[us]), "cudaEventSynchronize");
     const int nbx = (Hx + cs.batchSize2.x - 1) / cs.batchSize2.x;
     for (size_t i = 0; i < seeds.size(); i++) {
         std::mt19937 sub(seeds[i]);
         const int px = (int)(i % nbx) * cs.batchSize2.x, py = (int)(i / nbx) * cs.batchSize2.y;
         for (int x = px; x < std::min(Hx, px + cs.batchSize2.x); x++)
             for (int y = py; y < std::min(Hy, py + cs.batchSize2.y); y++)
-                m.u01Host.ptr()[y + x * Hy] = std::generate_canonical<float, std::numeric_limits<float>::digits>(sub);
+                u01h[y + x * Hy] = std::generate_canonical<float, std::numeric_limits<float>::digits>(sub);
     }
-    cudaCheck(cudaMemcpyAsync(m.u01.ptr(), m.u01Host.ptr(), ncols * sizeof(float), cudaMemcpyHostToDevice, ctx.stream), "u01 H2D");
-    cudaCheck(cudaEventRecord(m.u01Free, ctx.stream), "cudaEventRecord");
+    cudaCheck(cudaMemcpyAsync(m.u01.ptr(), u01h, ncols * sizeof(float), cudaMemcpyHostToDevice, ctx.stream), "u01 H2D");
+    cudaCheck(cudaEventRecord(m.u01Free[us], ctx.stream), "cudaEventRecord");
 
     ogn_actor_args a;
     std::memset(&a, 0, sizeof(a));
@@ -129,6 +137,15 @@ void Actor::stepDevice(ComputeSystem &cs, const int *const *inputDev, const int 
     // --- learn on historyIters random past samples (K11)
     if (learnEnabled && m.historySize > minSteps + 1) {
         std::uniform_int_distribution<int> historyDist(minSteps, m.historySize - 2);
+        ogn_actor_batch batch;
+        std::memset(&batch, 0, sizeof(batch));
+        auto flush = [&]() {
+            if (batch.n == 0) return;
+            LaunchScope ls(ctx, kActorLearn);
+            kernelCheck(ogn_actor_learn(&a, &batch, Hx, Hy, Hz, m.values.ptr(), alpha, beta, mimic ? 1 : 0, m.acts.ptr(), ctx.stream),
+                        "actor_learn");
+            batch.n = 0;
+        };
         for (int it = 0; it < historyIters; it++) {
             const int idx = historyDist(cs.rng);
             const int sPrev = m.slot(idx + 1), s = m.slot(idx);
@@ -138,13 +155,15 @@ void Actor::stepDevice(ComputeSystem &cs, const int *const *inputDev, const int 
                 g *= gamma;
             }
             consumeKernel2(cs, Hx, Hy);
+            ogn_actor_sample &S = batch.it[batch.n++];
             for (int v = 0; v < nvl; v++)
-                a.vl[v].cs = m.histInput[v].ptr() + (size_t)sPrev * visibleLayerDescs[v].size.x * visibleLayerDescs[v].size.y;
-            { LaunchScope ls(ctx, kActorLearn);
-            kernelCheck(ogn_actor_learn(&a, Hx, Hy, Hz, m.histTarget.ptr() + (size_t)s * ncols,
-                                        m.histValues.ptr() + (size_t)sPrev * ncols, m.values.ptr(), q, g, alpha, beta, mimic ? 1 : 0,
-                                        m.acts.ptr(), ctx.stream), "actor_learn"); }
+                S.cs[v] = m.histInput[v].ptr() + (size_t)sPrev * visibleLayerDescs[v].size.x * visibleLayerDescs[v].size.y;
+            S.target_prev = m.histTarget.ptr() + (size_t)s * ncols;
+            S.values_prev = m.histValues.ptr() + (size_t)sPrev * ncols;
+            S.q = q; S.g = g;
+            if (batch.n == OGN_MAX_ACTOR_SAMPLES) flush();
         }
+        flush();
         std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
     }
 }

@@ -65,11 +65,16 @@ struct Actor::Impl {
     std::vector<float> rewards;                 // [capacity]
     std::vector<detail::DevBuf<int>> inStage;
     detail::DevBuf<int> targetStage;
-    cudaEvent_t u01Free = nullptr;              // the pinned u01 staging may be rewritten after this event
+    static constexpr int kU01Slots = 4;         // pinned u01 staging ring: the host may queue this many steps ahead
+    cudaEvent_t u01Free[kU01Slots] = {};        // slot k may be rewritten after u01Free[k]
+    int u01Slot = 0;
     bool csDirty = true, valDirty = true;
     std::vector<char> wDirty;
 
-    ~Impl() { if (u01Free) cudaEventDestroy(u01Free); }
+    ~Impl() {
+        for (auto e : u01Free)
+            if (e) cudaEventDestroy(e);
+    }
     int slot(int logical) const { return (start + logical) % capacity; }
     void allocate(ComputeSystem &cs, const Int3 &hidden, int historyCapacity, const std::vector<VisibleLayerDesc> &vlds);
 };

@@ -440,51 +440,77 @@ k_pred_step(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int Hz, int
 // Actor. One pack group per hidden-y pack of action columns (template G from the action Z). The value matrix has
 // Hz = 1, i.e. its own geometry with pack factor 4: lane 0 of every column gathers the value row with the generic
 // single-lane routines below (action layers are tiny; SURVEY.md: "negligible bytes, correctness-critical RNG").
-__device__ __forceinline__ float value_row_sum(const ogn_rf &rf, const float *wv, const int *cs, int ox, int oy, int *countOut) {
+// Value row of one action column (the value matrix has Hz = 1): Σ over the column's field of W_v[slot][cs[slot]] in slot
+// order (Actor.cpp:27-33 / :105-111). The G lanes of the column's group cooperate: lane s % G loads slot s (its CSDR
+// read and its weight, 8 independent chains in flight per lane), the ordered sum is rebuilt with shuffles, so every lane
+// returns the same bits the sequential loop produces.
+template <int G>
+__device__ __forceinline__ float value_row_sum(unsigned sm, int hl, bool valid, const ogn_rf &rf, const float *wv, const int *cs, int ox,
+                                               int oy, int *countOut) {
     const int q = oy / rf.pf, p = oy % rf.pf;
     const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
     const int lyU = __ldg(rf.loyf + q), nyU = __ldg(rf.nyf + q);
     const float *w = wv + f_block(rf, ox, q) + p;
+    const int n = valid ? nxv * nyv : 0;
     float sum = 0.0f;
-    for (int dx = 0; dx < nxv; ++dx)
-        for (int dy = 0; dy < nyv; ++dy) {
-            const int c = __ldg(cs + (lx + dx) * rf.Vy + ly + dy);
-            sum += w[((long long)(dx * nyU + (ly + dy - lyU)) * rf.Vz + c) * rf.pf];
+    for (int s0 = 0; s0 < n; s0 += G * 8) {
+        float w8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int s = s0 + k * G + hl;
+            w8[k] = 0.0f;
+            if (s < n) {
+                const int dx = s / nyv, dy = s - dx * nyv;
+                const int c = __ldg(cs + (lx + dx) * rf.Vy + ly + dy);
+                w8[k] = w[((long long)(dx * nyU + (ly + dy - lyU)) * rf.Vz + c) * rf.pf];
+            }
         }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const float v = __shfl_sync(sm, w8[k], j, G);
+                if (s0 + k * G + j < n) sum += v;
+            }
+    }
     *countOut = nxv * nyv;
     return sum;
 }
-__device__ __forceinline__ void value_row_delta(const ogn_rf &rf, float *wv, const int *cs, int ox, int oy, float delta) {
+// W_v[slot][cs[slot]] += delta over the column's field (Actor.cpp:117-118); lane s % G owns slot s, as above
+template <int G>
+__device__ __forceinline__ void value_row_delta(int hl, bool valid, const ogn_rf &rf, float *wv, const int *cs, int ox, int oy, float delta) {
     const int q = oy / rf.pf, p = oy % rf.pf;
     const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), ly = __ldg(rf.loy + oy), nyv = __ldg(rf.ny + oy);
     const int lyU = __ldg(rf.loyf + q), nyU = __ldg(rf.nyf + q);
     float *w = wv + f_block(rf, ox, q) + p;
-    for (int dx = 0; dx < nxv; ++dx)
-        for (int dy = 0; dy < nyv; ++dy) {
-            const int c = __ldg(cs + (lx + dx) * rf.Vy + ly + dy);
-            w[((long long)(dx * nyU + (ly + dy - lyU)) * rf.Vz + c) * rf.pf] += delta;
-        }
+    const int n = valid ? nxv * nyv : 0;
+    for (int s = hl; s < n; s += G) {
+        const int dx = s / nyv, dy = s - dx * nyv;
+        const int c = __ldg(cs + (lx + dx) * rf.Vy + ly + dy);
+        w[((long long)(dx * nyU + (ly + dy - lyU)) * rf.Vz + c) * rf.pf] += delta;
+    }
 }
 
-// value (lane 0 of the column, broadcast) and the total slot count
+// value of the column (identical on every lane of its group) and the total slot count; cs0 != nullptr overrides the
+// visible layers' CSDR pointers (history samples)
 template <int G>
-__device__ __forceinline__ float actor_value(unsigned sm, int hl, bool colValid, const ogn_actor_args &A, int ox, int oy, int *countOut) {
+__device__ __forceinline__ float actor_value(unsigned sm, int hl, bool colValid, const ogn_actor_args &A, const int *const *csv, int ox,
+                                             int oy, int *countOut) {
     float value = 0.0f;
     int count = 0;
-    if (hl == 0 && colValid)
-        for (int v = 0; v < A.nvl; ++v) {
-            int n;
-            value += value_row_sum(A.geo[A.vl[v].geo_v], A.vl[v].wv, A.vl[v].cs, ox, oy, &n);
-            count += n;
-        }
-    *countOut = __shfl_sync(sm, count, 0, G);
-    return __shfl_sync(sm, value, 0, G);
+    for (int v = 0; v < A.nvl; ++v) {
+        int n;
+        value += value_row_sum<G>(sm, hl, colValid, A.geo[A.vl[v].geo_v], A.vl[v].wv, csv[v], ox, oy, &n);
+        count += n;
+    }
+    *countOut = count;
+    return value;
 }
 
 // raw action activations (Σ_v gather) / count into acts[] (column base)
 template <int G>
 __device__ __forceinline__ void actor_action_acts(unsigned gm, unsigned sm, int gl, int p, int hl, bool colValid, const ogn_actor_args &A,
-                                                  int ox, int q, int Hz, int count, float *acts) {
+                                                  const int *const *csv, int ox, int q, int Hz, int count, float *acts) {
     constexpr int P = Pack<G>::P;
     for (int hc0 = 0; hc0 < Hz; hc0 += G) {
         const int hc = hc0 + hl;
@@ -495,7 +521,7 @@ __device__ __forceinline__ void actor_action_acts(unsigned gm, unsigned sm, int 
             const ogn_rf &rf = A.geo[A.vl[v].geo_a];
             const PackCtx c = pack_ctx(rf, ox, q, p);
             const float *w = A.vl[v].wa + c.blk + p * Hz + hcl;
-            sum += gather_pack<G, false>(gm, gl, w, A.vl[v].cs, c, rf.Vy, rf.Vz, P * Hz);
+            sum += gather_pack<G, false>(gm, gl, w, csv[v], c, rf.Vy, rf.Vz, P * Hz);
         }
         sum = sum / (float)count;
         if (act) acts[hc] = sum;
@@ -530,12 +556,15 @@ k_actor_forward(const __grid_constant__ ogn_actor_args A, int Hx, int Hy, int Hz
     const int p = gl / G, hl = gl % G;
     const int oy = q * P + p;
     const bool colValid = oy < Hy;
-    const int col = ox * Hy + (colValid ? oy : Hy - 1);
+    const int oyc = colValid ? oy : Hy - 1;
+    const int col = ox * Hy + oyc;
+    const int *csv[OGN_MAX_PRED_VL];
+    for (int v = 0; v < A.nvl; ++v) csv[v] = A.vl[v].cs;
     int count;
-    const float value = actor_value<G>(sm, hl, colValid, A, ox, oy, &count);
+    const float value = actor_value<G>(sm, hl, colValid, A, csv, ox, oyc, &count);
     if (hl == 0 && colValid) hiddenValues[col] = value / (float)count;
     float *acts = hiddenActs + (long long)col * Hz;
-    actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, ox, q, Hz, count, acts);
+    actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, csv, ox, q, Hz, count, acts);
     if (!colValid) return;
     const float total = actor_softmax<G>(sm, hl, Hz, acts);
     if (hl == 0) {
@@ -551,12 +580,13 @@ k_actor_forward(const __grid_constant__ ogn_actor_args A, int Hx, int Hy, int Hz
     }
 }
 
-// K11: Actor::learn (Actor.cpp:92-185)
+// K11: Actor::learn (Actor.cpp:92-185) on B.n history samples, one after the other, in ONE launch: every action column
+// owns its value row and its action rows, so a column's lanes can walk the samples on their own (the reference launches
+// one kernel per sample; the result is the same because nothing crosses columns).
 template <int G>
 __global__ void __launch_bounds__(kThreads)
-k_actor_learn(const __grid_constant__ ogn_actor_args A, int Hx, int Hy, int Hz, int npacks, int packsPerRow,
-              const int *__restrict__ targetPrev, const float *__restrict__ valuesPrev, const float *__restrict__ hiddenValues, float q_,
-              float g, float alpha, float beta, int mimic, float *hiddenActs) {
+k_actor_learn(const __grid_constant__ ogn_actor_args A, const __grid_constant__ ogn_actor_batch B, int Hx, int Hy, int Hz, int npacks,
+              int packsPerRow, const float *__restrict__ hiddenValues, float alpha, float beta, int mimic, float *hiddenActs) {
     constexpr int P = Pack<G>::P, GP = Pack<G>::GP;
     const int gl = threadIdx.x & (GP - 1);
     const int pack = (blockIdx.x * kThreads + threadIdx.x) / GP;
@@ -566,36 +596,40 @@ k_actor_learn(const __grid_constant__ ogn_actor_args A, int Hx, int Hy, int Hz, 
     const int p = gl / G, hl = gl % G;
     const int oy = q * P + p;
     const bool colValid = oy < Hy;
-    const int col = ox * Hy + (colValid ? oy : Hy - 1);
-
-    const float newValue = q_ + g * hiddenValues[col];
-    int count;
-    float value = actor_value<G>(sm, hl, colValid, A, ox, oy, &count);
-    value = value / (float)count;
-    const float tdErrorValue = newValue - value;
-    const float deltaValue = alpha * tdErrorValue;
-    if (hl == 0 && colValid)
-        for (int v = 0; v < A.nvl; ++v) value_row_delta(A.geo[A.vl[v].geo_v], A.vl[v].wv, A.vl[v].cs, ox, oy, deltaValue);
-    const float tdErrorAction = newValue - valuesPrev[col];
-    const int target = targetPrev[col];
+    const int oyc = colValid ? oy : Hy - 1;
+    const int col = ox * Hy + oyc;
     float *acts = hiddenActs + (long long)col * Hz;
-    actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, ox, q, Hz, count, acts);
-    float total = 1.0f;
-    if (colValid) total = actor_softmax<G>(sm, hl, Hz, acts);
-    for (int hc0 = 0; hc0 < Hz; hc0 += G) {
-        const int hc = hc0 + hl;
-        const bool act = hc < Hz && colValid;
-        const int hcl = hc < Hz ? hc : Hz - 1;
-        float delta = 0.0f;
-        if (act)
-            delta = (mimic ? beta : (tdErrorAction > 0.0f ? beta : -beta)) *
-                    ((hc == target ? 1.0f : 0.0f) - __ldcg(acts + hc) / fmaxf(0.0001f, total));
-        for (int v = 0; v < A.nvl; ++v) {
-            const ogn_rf &rf = A.geo[A.vl[v].geo_a];
-            const PackCtx c = pack_ctx(rf, ox, q, p);
-            float *w = A.vl[v].wa + c.blk + p * Hz + hcl;
-            delta_pack<G>(gm, gl, act, w, A.vl[v].cs, delta, c, rf.Vy, rf.Vz, P * Hz);
+
+    for (int it = 0; it < B.n; ++it) {
+        const ogn_actor_sample &S = B.it[it];
+        const float newValue = S.q + S.g * hiddenValues[col];
+        int count;
+        float value = actor_value<G>(sm, hl, colValid, A, S.cs, ox, oyc, &count);
+        value = value / (float)count;
+        const float tdErrorValue = newValue - value;
+        const float deltaValue = alpha * tdErrorValue;
+        for (int v = 0; v < A.nvl; ++v) value_row_delta<G>(hl, colValid, A.geo[A.vl[v].geo_v], A.vl[v].wv, S.cs[v], ox, oyc, deltaValue);
+        const float tdErrorAction = newValue - S.values_prev[col];
+        const int target = S.target_prev[col];
+        actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, S.cs, ox, q, Hz, count, acts);
+        float total = 1.0f;
+        if (colValid) total = actor_softmax<G>(sm, hl, Hz, acts);
+        for (int hc0 = 0; hc0 < Hz; hc0 += G) {
+            const int hc = hc0 + hl;
+            const bool act = hc < Hz && colValid;
+            const int hcl = hc < Hz ? hc : Hz - 1;
+            float delta = 0.0f;
+            if (act)
+                delta = (mimic ? beta : (tdErrorAction > 0.0f ? beta : -beta)) *
+                        ((hc == target ? 1.0f : 0.0f) - __ldcg(acts + hc) / fmaxf(0.0001f, total));
+            for (int v = 0; v < A.nvl; ++v) {
+                const ogn_rf &rf = A.geo[A.vl[v].geo_a];
+                const PackCtx c = pack_ctx(rf, ox, q, p);
+                float *w = A.vl[v].wa + c.blk + p * Hz + hcl;
+                delta_pack<G>(gm, gl, act, w, S.cs[v], delta, c, rf.Vy, rf.Vz, P * Hz);
+            }
         }
+        __syncwarp(gm); // this sample's weight and scratch writes are ordered before the next sample's reads
     }
 }
 
@@ -965,15 +999,14 @@ int ogn_actor_forward(const ogn_actor_args *args, int Hx, int Hy, int Hz, const 
     return launch_status();
 }
 
-int ogn_actor_learn(const ogn_actor_args *args, int Hx, int Hy, int Hz, const int *target_cs_prev, const float *hidden_values_prev,
-                    const float *hidden_values, float q, float g_, float alpha, float beta, int mimic, float *hidden_activations,
-                    void *stream) {
-    if (args->nvl > OGN_MAX_PRED_VL) return (int)cudaErrorInvalidValue;
+int ogn_actor_learn(const ogn_actor_args *args, const ogn_actor_batch *batch, int Hx, int Hy, int Hz, const float *hidden_values,
+                    float alpha, float beta, int mimic, float *hidden_activations, void *stream) {
+    if (args->nvl > OGN_MAX_PRED_VL || batch->n < 0 || batch->n > OGN_MAX_ACTOR_SAMPLES) return (int)cudaErrorInvalidValue;
+    if (batch->n == 0) return 0;
     const int g = group_lanes(Hz), P = pack_factor(g), ppr = (Hy + P - 1) / P, npacks = Hx * ppr;
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads));
-    OGN_DISPATCH_G(g, (k_actor_learn<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, npacks, ppr, target_cs_prev,
-                                                                                  hidden_values_prev, hidden_values, q, g_, alpha, beta,
-                                                                                  mimic, hidden_activations)));
+    OGN_DISPATCH_G(g, (k_actor_learn<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, *batch, Hx, Hy, Hz, npacks, ppr, hidden_values,
+                                                                                  alpha, beta, mimic, hidden_activations)));
     return launch_status();
 }
 

@@ -70,3 +70,41 @@ def test_learning_disabled_and_params(product, oracle):
         b.step(ins, learn)
     d = diff_snapshots(a.snapshot(True), b.snapshot(True))
     assert not d, f"[checker={kind}] {d[:3]}"
+
+
+def test_actor_more_history_samples_than_one_launch_holds(product, oracle):
+    """historyIters above OGN_MAX_ACTOR_SAMPLES (16): the batched Actor learn must split into several launches and still
+    apply the samples in the reference's order."""
+    flat, kind = oracle
+    flat.set_num_threads(1)
+    cfg = configs.c3_actor(8)
+    from common import make_inputs, diff_snapshots, reward_at
+    a, b = maker(product.lib())(cfg), maker(flat)(cfg)
+    for h in (a, b):
+        h.setActorParams(1, 0.01, 0.01, 0.99, 4, 21)
+    action = None
+    for t in range(60):
+        ins = make_inputs(cfg, t, action)
+        a.step(ins, True, reward_at(t), False)
+        b.step(ins, True, reward_at(t), False)
+        action = b.getPredictionCs(1)
+        assert np.array_equal(a.getPredictionCs(1), action), f"[checker={kind}] action differs at step {t}"
+    d = diff_snapshots(a.snapshot(True), b.snapshot(True))
+    assert not d, f"[checker={kind}] {d[:3]}"
+
+
+@pytest.mark.parametrize("env", [
+    {"OGN_KERNELS": "scalar"}, {"OGN_KERNELS": "vec2"}, {"OGN_KERNELS": "pipe4"}, {"OGN_KERNELS": "pipe6"},
+    {"OGN_GRAPHS": "0"}, {"OGN_SIDE_STREAM": "1"},
+], ids=lambda e: "-".join(f"{k[4:].lower()}={v}" for k, v in e.items()))
+def test_every_kernel_variant_and_scheduling_mode_is_bit_exact(env):
+    """The alternative kernels (generic one-cell-per-lane, deeper register batches, cp.async rings) and scheduling modes
+    (no CUDA graphs, side stream on one GPU) are selected per process: rerun a parity subset in a subprocess for each."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+           "-k", "c2_video_small or c4_large_layer_small or c1_sine or odd"]
+    r = subprocess.run(cmd, cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
