@@ -287,24 +287,44 @@ def main():
         opt = og.CreateOptions(device=local_rank, deviceInit=cfg["device_init"], replayRng=False, shardRank=rank, shardWorld=world,
                                peerExchange=peer)
     ext = {}
-    if world > 1 and not peer and not ens:
-        cache = {}
 
-        def all_gather(buf, count, stream_ptr):
-            key = (buf, count)
-            if key not in cache:
-                full = torch.as_tensor(_DevArray(buf, count * world), device=f"cuda:{local_rank}")
-                cache[key] = (full, full[rank * count:(rank + 1) * count])
-            full, mine = cache[key]
-            with torch.cuda.stream(ext["s"]):
-                dist.all_gather_into_tensor(full, mine)
-        opt.allGather = all_gather
-    h = og.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=cfg["seed"], options=opt)
-    ext["s"] = torch.cuda.ExternalStream(h.stream(), device=local_rank)
+    def make_hierarchy(use_peer):
+        if not ens:
+            opt.peerExchange = use_peer
+            opt.allGather = None
+        if world > 1 and not use_peer and not ens:
+            cache = {}
+
+            def all_gather(buf, count, stream_ptr):
+                key = (buf, count)
+                if key not in cache:
+                    full = torch.as_tensor(_DevArray(buf, count * world), device=f"cuda:{local_rank}")
+                    cache[key] = (full, full[rank * count:(rank + 1) * count])
+                full, mine = cache[key]
+                with torch.cuda.stream(ext["s"]):
+                    dist.all_gather_into_tensor(full, mine)
+            opt.allGather = all_gather
+        hh = og.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=cfg["seed"], options=opt)
+        ext["s"] = torch.cuda.ExternalStream(hh.stream(), device=local_rank)
+        return hh
+
+    h = make_hierarchy(peer)
     if peer:  # one CUDA IPC handle per rank, gathered over the process group; after this the step path never calls NCCL
-        handles = [None] * world
-        dist.all_gather_object(handles, h.peerExport())
-        h.peerAttach(handles)
+        ok = 1
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, h.peerExport())
+            h.peerAttach(handles)
+        except Exception as e:  # CUDA IPC unavailable (e.g. no shared IPC namespace): fall back to NCCL on every rank
+            print(f"bench.py: rank {rank}: peer-memory exchange unavailable ({e}); using NCCL all-gather", file=sys.stderr)
+            ok = 0
+        t = torch.tensor([ok], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 0:
+            h.close()
+            del h
+            peer = False
+            h = make_hierarchy(False)
         dist.barrier()
     h.synchronize()
 
