@@ -508,10 +508,13 @@ __device__ __forceinline__ float actor_value(unsigned sm, int hl, bool colValid,
 }
 
 // raw action activations (Σ_v gather) / count into acts[] (column base)
+// Returns the lane's own activation of the first chunk (hc = hl), which is all of them when Hz <= G; acts[] is written
+// only when Hz > G (the softmax then goes through that scratch).
 template <int G>
-__device__ __forceinline__ void actor_action_acts(unsigned gm, unsigned sm, int gl, int p, int hl, bool colValid, const ogn_actor_args &A,
-                                                  const int *const *csv, int ox, int q, int Hz, int count, float *acts) {
+__device__ __forceinline__ float actor_action_acts(unsigned gm, unsigned sm, int gl, int p, int hl, bool colValid, const ogn_actor_args &A,
+                                                   const int *const *csv, int ox, int q, int Hz, int count, float *acts) {
     constexpr int P = Pack<G>::P;
+    float mine = 0.0f;
     for (int hc0 = 0; hc0 < Hz; hc0 += G) {
         const int hc = hc0 + hl;
         const bool act = hc < Hz && colValid;
@@ -524,9 +527,23 @@ __device__ __forceinline__ void actor_action_acts(unsigned gm, unsigned sm, int 
             sum += gather_pack<G, false>(gm, gl, w, csv[v], c, rf.Vy, rf.Vz, P * Hz);
         }
         sum = sum / (float)count;
-        if (act) acts[hc] = sum;
+        if (hc0 == 0) mine = sum;
+        if (act && Hz > G) acts[hc] = sum;
     }
     __syncwarp(sm);
+    return mine;
+}
+
+// The same softmax when the column's Hz cells sit one per lane (Hz <= G): the max and the ascending-order sum are rebuilt
+// with shuffles, nothing goes through memory. e = this lane's numerator expf(act - max) (0 for lanes past Hz).
+template <int G>
+__device__ __forceinline__ float actor_softmax_lanes(unsigned sm, int hl, int Hz, float act, float &e) {
+    float m = -999999.0f;
+    for (int hc = 0; hc < Hz; ++hc) m = fmaxf(m, __shfl_sync(sm, act, hc, G));
+    e = hl < Hz ? ogn_expf(act - m) : 0.0f;
+    float total = 0.0f;
+    for (int hc = 0; hc < Hz; ++hc) total += __shfl_sync(sm, e, hc, G);
+    return total;
 }
 
 // softmax numerators in place (Actor.cpp:57-69 / :159-171): acts[hc] = expf(acts[hc] - max); returns Σ in ascending hc order.
@@ -564,11 +581,26 @@ k_actor_forward(const __grid_constant__ ogn_actor_args A, int Hx, int Hy, int Hz
     const float value = actor_value<G>(sm, hl, colValid, A, csv, ox, oyc, &count);
     if (hl == 0 && colValid) hiddenValues[col] = value / (float)count;
     float *acts = hiddenActs + (long long)col * Hz;
-    actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, csv, ox, q, Hz, count, acts);
+    const float mine = actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, csv, ox, q, Hz, count, acts);
     if (!colValid) return;
+    if (Hz <= G) {
+        float e;
+        const float total = actor_softmax_lanes<G>(sm, hl, Hz, mine, e);
+        if (hl < Hz) acts[hl] = e; // hiddenActivations keeps the numerators (Actor.cpp:66)
+        // std::uniform_real_distribution<float>(0, total): canonical * (b - a) + a   (libstdc++ bits/random.h)
+        const float cusp = u01[col] * (total - 0.0f) + 0.0f;
+        int select = 0;
+        float sumSoFar = 0.0f;
+        bool found = false;
+        for (int hc = 0; hc < Hz; ++hc) { // every lane replays the scan (the shuffles need all of them)
+            sumSoFar += __shfl_sync(sm, e, hc, G);
+            if (!found && sumSoFar >= cusp) { select = hc; found = true; }
+        }
+        if (hl == 0) hiddenCs[col] = select;
+        return;
+    }
     const float total = actor_softmax<G>(sm, hl, Hz, acts);
     if (hl == 0) {
-        // std::uniform_real_distribution<float>(0, total): canonical * (b - a) + a   (libstdc++ bits/random.h)
         const float cusp = u01[col] * (total - 0.0f) + 0.0f;
         int select = 0;
         float sumSoFar = 0.0f;
@@ -611,9 +643,14 @@ k_actor_learn(const __grid_constant__ ogn_actor_args A, const __grid_constant__ 
         for (int v = 0; v < A.nvl; ++v) value_row_delta<G>(hl, colValid, A.geo[A.vl[v].geo_v], A.vl[v].wv, S.cs[v], ox, oyc, deltaValue);
         const float tdErrorAction = newValue - S.values_prev[col];
         const int target = S.target_prev[col];
-        actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, S.cs, ox, q, Hz, count, acts);
-        float total = 1.0f;
-        if (colValid) total = actor_softmax<G>(sm, hl, Hz, acts);
+        const float mine = actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, S.cs, ox, q, Hz, count, acts);
+        float total = 1.0f, e = 0.0f;
+        const bool lanes = Hz <= G; // one cell per lane: softmax through shuffles, else through the acts[] scratch
+        if (lanes) {
+            total = actor_softmax_lanes<G>(sm, hl, Hz, mine, e);
+            if (hl < Hz && colValid) acts[hl] = e;
+        } else if (colValid)
+            total = actor_softmax<G>(sm, hl, Hz, acts);
         for (int hc0 = 0; hc0 < Hz; hc0 += G) {
             const int hc = hc0 + hl;
             const bool act = hc < Hz && colValid;
@@ -621,7 +658,7 @@ k_actor_learn(const __grid_constant__ ogn_actor_args A, const __grid_constant__ 
             float delta = 0.0f;
             if (act)
                 delta = (mimic ? beta : (tdErrorAction > 0.0f ? beta : -beta)) *
-                        ((hc == target ? 1.0f : 0.0f) - __ldcg(acts + hc) / fmaxf(0.0001f, total));
+                        ((hc == target ? 1.0f : 0.0f) - (lanes ? e : __ldcg(acts + hc)) / fmaxf(0.0001f, total));
             for (int v = 0; v < A.nvl; ++v) {
                 const ogn_rf &rf = A.geo[A.vl[v].geo_a];
                 const PackCtx c = pack_ctx(rf, ox, q, p);

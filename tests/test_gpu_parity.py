@@ -108,3 +108,25 @@ def test_every_kernel_variant_and_scheduling_mode_is_bit_exact(env):
            "-k", "c2_video_small or c4_large_layer_small or c1_sine or odd"]
     r = subprocess.run(cmd, cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_parameter_changes_mid_run_with_graph_replay(product, oracle):
+    """Hyper-parameters and learnEnabled change while the captured step graphs are being replayed: the graph key must
+    pick up every change (alpha is a kernel argument baked into a captured launch)."""
+    flat, kind = oracle
+    cfg = configs.c2_video(8, 3)
+    from common import make_inputs, diff_snapshots
+    a, b = maker(product.lib())(cfg), maker(flat)(cfg)
+    for t in range(96):
+        if t in (24, 48, 72):
+            for h in (a, b):
+                h.setSCAlpha(t // 24 % 3, 0.05 * (t // 24))
+                h.setPredAlpha(0, 0, 0.25 + 0.125 * (t // 24))
+        learn = not (40 <= t < 56)
+        ins = make_inputs(cfg, t)
+        a.step(ins, learn)
+        b.step(ins, learn)
+        if t % 8 == 7:
+            assert np.array_equal(a.getPredictionCs(0), b.getPredictionCs(0)), f"[checker={kind}] prediction differs at step {t}"
+    d = diff_snapshots(a.snapshot(True), b.snapshot(True))
+    assert not d, f"[checker={kind}] {d[:3]}"
