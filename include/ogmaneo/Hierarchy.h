@@ -95,6 +95,13 @@ public:
     void initRandomEnsemble(ComputeSystem &cs, const std::vector<unsigned> &seeds, const std::vector<Int3> &inputSizes,
                             const std::vector<InputType> &inputTypes, const std::vector<LayerDesc> &layerDescs);
     int getEnsembleSize() const;
+    // Checkpoint of hierarchies the reference's save format cannot hold (more than 2^31 weights per matrix, ensembles,
+    // x-slab shards: SURVEY.md §8f-1): 64-bit counts, weights streamed in their device layouts through pinned staging,
+    // one file per rank. Layout: "OGNCKPT1", the initRandom arguments, ensemble size and shard (rank, world), tick state,
+    // history rings, then SparseCoder / Predictor device state layer by layer. readCheckpoint rebuilds the hierarchy from
+    // the header (device-side init, then overwritten). Hierarchies with an Actor use writeToStream instead.
+    void writeCheckpoint(std::ostream &os, const std::vector<InputType> &inputTypes, const std::vector<LayerDesc> &layerDescs) const;
+    void readCheckpoint(std::istream &is, ComputeSystem &cs, std::vector<InputType> *inputTypesOut = nullptr);
     void readFromStream(std::istream &is, ComputeSystem &cs); // choose the device / stream to load onto
 
 private:

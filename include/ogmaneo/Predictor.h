@@ -3,6 +3,9 @@
 // K6+K7+K8 (include/ogn_kernels_api.h). Host members returned by getters are lazily refreshed mirrors.
 #pragma once
 
+#include <istream>
+#include <ostream>
+
 #include "ComputeSystem.h"
 
 namespace ogmaneo {
@@ -59,6 +62,10 @@ public:
     void stepDevice(ComputeSystem &cs, bool learn, const int *targetCsDevice, bool activate, const int *const *inputCsDevice,
                     bool deferExchange = false, bool onSideStream = false);
     const int *hiddenCsDevice() const;
+    // raw device state (weights in their device layouts, CSDRs, parities) of an already constructed layer of the same
+    // shape: the building block of Hierarchy::writeCheckpoint / readCheckpoint
+    void writeDeviceState(std::ostream &os) const;
+    void readDeviceState(std::istream &is);
     void readFromStream(std::istream &is, ComputeSystem &cs);
     void setState(const IntBuffer &hiddenCs, const std::vector<IntBuffer> &inputCsPrev);
 

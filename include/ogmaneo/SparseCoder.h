@@ -4,6 +4,9 @@
 // members returned by the getters are mirrors, refreshed lazily (a getter may synchronise the stream).
 #pragma once
 
+#include <istream>
+#include <ostream>
+
 #include "ComputeSystem.h"
 
 namespace ogmaneo {
@@ -64,6 +67,12 @@ public:
     void stateSignature(std::vector<int> &key) const; // everything that selects this layer's kernel arguments (graph cache key)
     void stepDevice(ComputeSystem &cs, const int *const *inputCsDevice, bool learnEnabled, int *copyOut);
     const int *hiddenCsDevice() const;
+    // raw device state (weights in their device layouts, CSDRs, parities) of an already constructed layer of the same
+    // shape: the building block of Hierarchy::writeCheckpoint / readCheckpoint
+    int shardRank() const;
+    int shardWorld() const;
+    void writeDeviceState(std::ostream &os) const;
+    void readDeviceState(std::istream &is);
     void readFromStream(std::istream &is, ComputeSystem &cs); // choose the device / stream to load onto
     void setHiddenState(const IntBuffer &hiddenCs, const IntBuffer &hiddenCsPrev);
 

@@ -55,6 +55,13 @@ uint64_t ogn_peer_take_wait_ns(void *h);
  * replicas). Returns non-zero if hidden_x is not a multiple of world. */
 int ogn_shard_plan(int hidden_x, int visible_x, int radius, int rank, int world, int out[6]);
 
+/* Checkpoints for hierarchies the reference's save format cannot hold (more than 2^31 weights per matrix, ensembles,
+ * shards): 64-bit counts, weights streamed in their device layouts, one file per rank (Hierarchy::writeCheckpoint).
+ * save returns the bytes written or -1. load rebuilds the hierarchy from the file's header; opt supplies the device and,
+ * for a sharded checkpoint, the same shard_rank / shard_world (and exchange settings) the file was written with. */
+int64_t ogn_checkpoint_save(void *h, const char *path);
+int ogn_checkpoint_load(const char *path, const ogn_create_options *opt, void **out);
+
 /* Hierarchy::step on inputs that already live in device memory (int32 [member][columns] per input). Fully asynchronous
  * on the hierarchy's stream: nothing is copied to or from the host. */
 int ogn_step_device(void *h, const int *const *input_cs_dev, int learn_enabled, float reward, int mimic);

@@ -402,6 +402,43 @@ void WeightSetArray::cloneFrom(DeviceContext &ctx, const WeightSetArray &o) {
     for (size_t i = 0; i < sets.size(); i++) sets[i].cloneFrom(ctx, o.sets[i]);
 }
 
+void writeDeviceRaw(std::ostream &os, DeviceContext &ctx, const void *dev, size_t bytes) {
+    const uint64_t n = bytes;
+    os.write(reinterpret_cast<const char *>(&n), sizeof(n));
+    if (!bytes) return;
+    ctx.joinSide();
+    const size_t chunk = std::min<size_t>(bytes, (size_t)64 << 20);
+    PinnedBuf<char> stage;
+    stage.alloc(chunk);
+    for (size_t off = 0; off < bytes; off += chunk) {
+        const size_t m = std::min(chunk, bytes - off);
+        cudaCheck(cudaMemcpyAsync(stage.ptr(), (const char *)dev + off, m, cudaMemcpyDeviceToHost, ctx.stream), "checkpoint D2H");
+        ctx.sync();
+        os.write(stage.ptr(), (std::streamsize)m);
+    }
+    if (!os) throw std::runtime_error("ogmaneo-b200: checkpoint write failed");
+}
+
+void readDeviceRaw(std::istream &is, DeviceContext &ctx, void *dev, size_t bytes) {
+    uint64_t n = 0;
+    is.read(reinterpret_cast<char *>(&n), sizeof(n));
+    if (!is || n != bytes)
+        throw std::runtime_error("ogmaneo-b200: checkpoint does not match this hierarchy (buffer of " + std::to_string(n) +
+                                 " bytes where " + std::to_string(bytes) + " are expected)");
+    if (!bytes) return;
+    ctx.joinSide();
+    const size_t chunk = std::min<size_t>(bytes, (size_t)64 << 20);
+    PinnedBuf<char> stage;
+    stage.alloc(chunk);
+    for (size_t off = 0; off < bytes; off += chunk) {
+        const size_t m = std::min(chunk, bytes - off);
+        is.read(stage.ptr(), (std::streamsize)m);
+        if (!is) throw std::runtime_error("ogmaneo-b200: checkpoint is truncated");
+        cudaCheck(cudaMemcpyAsync((char *)dev + off, stage.ptr(), m, cudaMemcpyHostToDevice, ctx.stream), "checkpoint H2D");
+        ctx.sync();
+    }
+}
+
 int geoIndex(ogn_rf *table, int &count, const Geometry &g) {
     for (int i = 0; i < count; i++)
         if (table[i].lox == g.host.lox) return i; // same device tables <=> same Geometry object

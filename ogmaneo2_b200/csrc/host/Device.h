@@ -7,6 +7,8 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <istream>
+#include <ostream>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -254,6 +256,16 @@ struct WeightSetArray {
     std::vector<WeightSet> sets;
     void cloneFrom(DeviceContext &ctx, const WeightSetArray &o);
 };
+
+// Raw device buffer <-> stream, 64-bit element count first, through a pinned staging buffer (checkpoints).
+void writeDeviceRaw(std::ostream &os, DeviceContext &ctx, const void *dev, size_t bytes);
+void readDeviceRaw(std::istream &is, DeviceContext &ctx, void *dev, size_t bytes);
+template <typename T> void writeDev(std::ostream &os, DeviceContext &ctx, const DevBuf<T> &b) {
+    writeDeviceRaw(os, ctx, b.ptr(), b.size() * sizeof(T));
+}
+template <typename T> void readDev(std::istream &is, DeviceContext &ctx, DevBuf<T> &b) {
+    readDeviceRaw(is, ctx, b.ptr(), b.size() * sizeof(T));
+}
 
 // Geometry table of one launch: returns the index of g in `table` (by-value ogn_rf copies), appending if new.
 int geoIndex(ogn_rf *table, int &count, const Geometry &g);

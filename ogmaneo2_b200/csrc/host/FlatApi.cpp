@@ -17,6 +17,7 @@ struct Handle {
     ComputeSystem cs;
     Hierarchy h;
     std::vector<InputType> types;
+    std::vector<Hierarchy::LayerDesc> lds; // empty when the handle came from ogn_load (the reference format has no descs)
 };
 thread_local std::string g_err;
 
@@ -68,6 +69,7 @@ int ogn_create_ex(const ogn_hierarchy_desc *d, uint32_t seed, const ogn_create_o
         H->cs.rng.seed(seed);
         std::vector<Int3> sizes; std::vector<Hierarchy::LayerDesc> lds;
         unpack(d, sizes, H->types, lds);
+        H->lds = lds;
         int ensemble = 1;
         if (opt) {
             H->cs.device = opt->device;
@@ -246,6 +248,46 @@ int ogn_load(const char *path, uint32_t seed, void **out) {
         H->cs.rng.seed(seed);
         H->cs.replayRng = true;
         H->h.readFromStream(is, H->cs);
+        *out = H.release();
+    });
+}
+int64_t ogn_checkpoint_save(void *h, const char *path) {
+    int64_t n = -1;
+    guard([&] {
+        Handle *H = (Handle *)h;
+        if (H->lds.empty()) throw std::runtime_error("checkpointing needs a handle made by ogn_create / ogn_create_ex / ogn_checkpoint_load");
+        std::ofstream os(path, std::ios::binary);
+        if (!os) throw std::runtime_error("cannot open file for writing");
+        H->h.writeCheckpoint(os, H->types, H->lds);
+        n = (int64_t)os.tellp();
+    });
+    return n;
+}
+int ogn_checkpoint_load(const char *path, const ogn_create_options *opt, void **out) {
+    *out = nullptr;
+    return guard([&] {
+        std::ifstream is(path, std::ios::binary);
+        if (!is) throw std::runtime_error("cannot open file");
+        std::unique_ptr<Handle> H(new Handle());
+        if (opt) {
+            H->cs.device = opt->device;
+            if (opt->replay_rng) H->cs.replayRng = true;
+            H->cs.shardRank = opt->shard_rank; H->cs.shardWorld = opt->shard_world > 0 ? opt->shard_world : 1;
+            H->cs.allGather = opt->all_gather; H->cs.allGatherUser = opt->all_gather_user;
+            H->cs.peerExchange = opt->peer_exchange != 0;
+        }
+        H->h.readCheckpoint(is, H->cs, &H->types);
+        // the layer descriptors travel in the file; keep them so that the handle can be checkpointed again
+        const int L = H->h.getNumLayers();
+        H->lds.resize(L);
+        is.clear();
+        is.seekg(8 + 5 * 4 + (std::streamoff)H->types.size() * 16);
+        for (int l = 0; l < L; l++) {
+            int32_t v[9];
+            is.read(reinterpret_cast<char *>(v), sizeof(v));
+            H->lds[l].hiddenSize = Int3(v[0], v[1], v[2]); H->lds[l].ffRadius = v[3]; H->lds[l].pRadius = v[4];
+            H->lds[l].ticksPerUpdate = v[5]; H->lds[l].temporalHorizon = v[6]; H->lds[l].aRadius = v[7]; H->lds[l].historyCapacity = v[8];
+        }
         *out = H.release();
     });
 }

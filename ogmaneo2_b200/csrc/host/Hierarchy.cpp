@@ -496,6 +496,91 @@ void Hierarchy::readFromStream(std::istream &is, ComputeSystem &cs) {
     }
 }
 
+// --- checkpoints (include/ogmaneo/Hierarchy.h) --------------------------------------------------------------------------
+namespace {
+const char kCkptMagic[8] = {'O', 'G', 'N', 'C', 'K', 'P', 'T', '1'};
+template <typename T> void put(std::ostream &os, const T &v) { os.write(reinterpret_cast<const char *>(&v), sizeof(T)); }
+template <typename T> T get(std::istream &is) {
+    T v{};
+    is.read(reinterpret_cast<char *>(&v), sizeof(T));
+    if (!is) throw std::runtime_error("ogmaneo-b200: checkpoint is truncated");
+    return v;
+}
+} // namespace
+
+void Hierarchy::writeCheckpoint(std::ostream &os, const std::vector<InputType> &inputTypes, const std::vector<LayerDesc> &lds) const {
+    const Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    for (auto &a : aLayers)
+        if (a) throw std::runtime_error("ogmaneo-b200: checkpoints do not cover Actor layers (use writeToStream)");
+    const int L = (int)scLayers.size(), NI = (int)inputSizes.size();
+    if ((int)inputTypes.size() != NI || (int)lds.size() != L) throw std::invalid_argument("ogmaneo-b200: checkpoint descriptors do not match");
+    os.write(kCkptMagic, sizeof(kCkptMagic));
+    put<int32_t>(os, NI); put<int32_t>(os, L); put<int32_t>(os, m.batch);
+    put<int32_t>(os, scLayers[0].shardRank()); put<int32_t>(os, scLayers[0].shardWorld());
+    for (int i = 0; i < NI; i++) { put<int32_t>(os, inputSizes[i].x); put<int32_t>(os, inputSizes[i].y); put<int32_t>(os, inputSizes[i].z); put<int32_t>(os, (int)inputTypes[i]); }
+    for (int l = 0; l < L; l++) {
+        const LayerDesc &d = lds[l];
+        const int32_t v[9] = {d.hiddenSize.x, d.hiddenSize.y, d.hiddenSize.z, d.ffRadius, d.pRadius, d.ticksPerUpdate, d.temporalHorizon, d.aRadius, d.historyCapacity};
+        os.write(reinterpret_cast<const char *>(v), sizeof(v));
+    }
+    for (int l = 0; l < L; l++) { put<int32_t>(os, ticks[l]); put<int32_t>(os, (int)updates[l]); }
+    for (int l = 0; l < L; l++)
+        for (const Ring &r : m.histories[l]) { put<int32_t>(os, r.T); put<int32_t>(os, r.start); writeDev(os, ctx, r.buf); }
+    for (int l = 0; l < L; l++) {
+        scLayers[l].writeDeviceState(os);
+        for (auto &p : pLayers[l])
+            if (p) p->writeDeviceState(os);
+    }
+    if (!os) throw std::runtime_error("ogmaneo-b200: checkpoint write failed");
+}
+
+void Hierarchy::readCheckpoint(std::istream &is, ComputeSystem &cs, std::vector<InputType> *typesOut) {
+    char magic[8];
+    is.read(magic, sizeof(magic));
+    if (!is || std::memcmp(magic, kCkptMagic, sizeof(magic)) != 0) throw std::runtime_error("ogmaneo-b200: not a checkpoint file");
+    const int NI = get<int32_t>(is), L = get<int32_t>(is), batch = get<int32_t>(is), rank = get<int32_t>(is), world = get<int32_t>(is);
+    if (rank != cs.shardRank || world != cs.shardWorld)
+        throw std::runtime_error("ogmaneo-b200: checkpoint of shard " + std::to_string(rank) + "/" + std::to_string(world) +
+                                 " loaded into shard " + std::to_string(cs.shardRank) + "/" + std::to_string(cs.shardWorld));
+    std::vector<Int3> sizes(NI);
+    std::vector<InputType> types(NI);
+    for (int i = 0; i < NI; i++) {
+        sizes[i].x = get<int32_t>(is); sizes[i].y = get<int32_t>(is); sizes[i].z = get<int32_t>(is);
+        types[i] = (InputType)get<int32_t>(is);
+    }
+    std::vector<LayerDesc> lds(L);
+    for (int l = 0; l < L; l++) {
+        int32_t v[9];
+        is.read(reinterpret_cast<char *>(v), sizeof(v));
+        lds[l].hiddenSize = Int3(v[0], v[1], v[2]); lds[l].ffRadius = v[3]; lds[l].pRadius = v[4]; lds[l].ticksPerUpdate = v[5];
+        lds[l].temporalHorizon = v[6]; lds[l].aRadius = v[7]; lds[l].historyCapacity = v[8];
+    }
+    // same shapes and allocations as initRandom; the weights are overwritten below, so the cheap device-side init will do
+    const bool savedInit = cs.deviceInit;
+    cs.deviceInit = true;
+    if (batch > 1) initRandomEnsemble(cs, std::vector<unsigned>(batch, 0u), sizes, types, lds);
+    else initRandom(cs, sizes, types, lds);
+    cs.deviceInit = savedInit;
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    for (int l = 0; l < L; l++) { ticks[l] = get<int32_t>(is); updates[l] = (char)get<int32_t>(is); }
+    for (int l = 0; l < L; l++)
+        for (Ring &r : m.histories[l]) {
+            const int T = get<int32_t>(is), start = get<int32_t>(is);
+            if (T != r.T) throw std::runtime_error("ogmaneo-b200: checkpoint history length mismatch");
+            r.start = start;
+            readDev(is, ctx, r.buf);
+        }
+    for (int l = 0; l < L; l++) {
+        scLayers[l].readDeviceState(is);
+        for (auto &p : pLayers[l])
+            if (p) p->readDeviceState(is);
+    }
+    if (typesOut) *typesOut = types;
+}
+
 void Hierarchy::readFromStream(std::istream &is) {
     ComputeSystem cs;
     if (impl) cs.device = impl->ctx->device;

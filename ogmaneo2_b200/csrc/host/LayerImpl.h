@@ -11,7 +11,7 @@ struct SparseCoder::Impl {
     std::shared_ptr<detail::DeviceContext> ctx;
     int batch = 1;          // ensemble members stepped in lockstep
     int x0 = 0, x1 = 0;     // hidden x-slab owned by this device
-    int world = 1;
+    int world = 1, rank = 0;
     detail::WeightSetArray ws;
     // hiddenCs / hiddenCsPrev ping-pong: cs_[cur] is hiddenCs; hiddenCsPrev is the same buffer after a step (the
     // reference copies hiddenCs -> hiddenCsPrev at the end of step()) or the other one after setState().

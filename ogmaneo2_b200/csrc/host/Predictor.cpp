@@ -278,6 +278,36 @@ void Predictor::setState(const IntBuffer &hc, const std::vector<IntBuffer> &prev
 
 const int *Predictor::hiddenCsDevice() const { return impl->hiddenCs.ptr(); }
 
+void Predictor::writeDeviceState(std::ostream &os) const {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    const int hdr[3] = {m.prevCur, m.x0, m.x1};
+    os.write(reinterpret_cast<const char *>(hdr), sizeof(hdr));
+    os.write(reinterpret_cast<const char *>(&alpha), sizeof(alpha));
+    writeDev(os, ctx, m.acts); writeDev(os, ctx, m.hiddenCs);
+    for (int p = 0; p < 2; p++)
+        for (const auto &b : m.prev_[p]) writeDev(os, ctx, b);
+    for (const WeightSet &w : m.ws.sets) writeDev(os, ctx, w.wf);
+}
+
+void Predictor::readDeviceState(std::istream &is) {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    int hdr[3] = {0, 0, 0};
+    is.read(reinterpret_cast<char *>(hdr), sizeof(hdr));
+    if (hdr[1] != m.x0 || hdr[2] != m.x1) throw std::runtime_error("ogmaneo-b200: checkpoint was written by a different shard");
+    m.prevCur = hdr[0];
+    is.read(reinterpret_cast<char *>(&alpha), sizeof(alpha));
+    readDev(is, ctx, m.acts); readDev(is, ctx, m.hiddenCs);
+    for (int p = 0; p < 2; p++)
+        for (auto &b : m.prev_[p]) readDev(is, ctx, b);
+    for (WeightSet &w : m.ws.sets) readDev(is, ctx, w.wf);
+    m.csDirty = m.actDirty = m.prevDirty = true;
+    std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
+}
+
 void Predictor::stateSignature(std::vector<int> &key) const {
     key.push_back(impl->prevCur);
     int a;

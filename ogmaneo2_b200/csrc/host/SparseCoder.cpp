@@ -20,7 +20,7 @@ SparseCoder &SparseCoder::operator=(const SparseCoder &o) {
         DeviceContext &ctx = *o.impl->ctx;
         cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
         impl->ctx = o.impl->ctx; impl->batch = o.impl->batch; impl->x0 = o.impl->x0; impl->x1 = o.impl->x1;
-        impl->world = o.impl->world; impl->cur = o.impl->cur; impl->prevAliasesCur = o.impl->prevAliasesCur;
+        impl->world = o.impl->world; impl->rank = o.impl->rank; impl->cur = o.impl->cur; impl->prevAliasesCur = o.impl->prevAliasesCur;
         impl->csDirty = o.impl->csDirty; impl->wDirty = o.impl->wDirty; impl->reconDirty = o.impl->reconDirty;
         impl->ws.cloneFrom(ctx, o.impl->ws);
         impl->cs_[0].cloneFrom(o.impl->cs_[0], ctx.stream); impl->cs_[1].cloneFrom(o.impl->cs_[1], ctx.stream);
@@ -35,7 +35,7 @@ SparseCoder &SparseCoder::operator=(const SparseCoder &o) {
 
 void SparseCoder::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, const std::vector<VisibleLayerDesc> &vlds, int batch_) {
     ctx = cs.sharedContext();
-    batch = batch_; world = cs.shardWorld;
+    batch = batch_; world = cs.shardWorld; rank = cs.shardRank;
     slabOf(hidden.x, cs.shardRank, cs.shardWorld, x0, x1);
     ws.sets.clear(); ws.sets.resize(vlds.size());
     for (size_t v = 0; v < vlds.size(); v++)
@@ -314,6 +314,35 @@ void SparseCoder::setHiddenState(const IntBuffer &hc, const IntBuffer &hcPrev) {
 }
 
 const int *SparseCoder::hiddenCsDevice() const { return impl->cs_[impl->cur].ptr(); }
+
+int SparseCoder::shardRank() const { return impl->rank; }
+int SparseCoder::shardWorld() const { return impl->world; }
+
+void SparseCoder::writeDeviceState(std::ostream &os) const {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    const int hdr[4] = {m.cur, m.prevAliasesCur ? 1 : 0, m.x0, m.x1};
+    os.write(reinterpret_cast<const char *>(hdr), sizeof(hdr));
+    os.write(reinterpret_cast<const char *>(&alpha), sizeof(alpha));
+    writeDev(os, ctx, m.cs_[0]); writeDev(os, ctx, m.cs_[1]);
+    for (const WeightSet &w : m.ws.sets) { writeDev(os, ctx, w.wf); writeDev(os, ctx, w.wr); writeDev(os, ctx, w.recon); }
+}
+
+void SparseCoder::readDeviceState(std::istream &is) {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    int hdr[4] = {0, 0, 0, 0};
+    is.read(reinterpret_cast<char *>(hdr), sizeof(hdr));
+    if (hdr[2] != m.x0 || hdr[3] != m.x1) throw std::runtime_error("ogmaneo-b200: checkpoint was written by a different shard");
+    m.cur = hdr[0]; m.prevAliasesCur = hdr[1] != 0;
+    is.read(reinterpret_cast<char *>(&alpha), sizeof(alpha));
+    readDev(is, ctx, m.cs_[0]); readDev(is, ctx, m.cs_[1]);
+    for (WeightSet &w : m.ws.sets) { readDev(is, ctx, w.wf); readDev(is, ctx, w.wr); readDev(is, ctx, w.recon); }
+    m.csDirty = m.reconDirty = true;
+    std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
+}
 
 void SparseCoder::stateSignature(std::vector<int> &key) const {
     key.push_back(impl->cur); key.push_back(impl->prevAliasesCur ? 1 : 0);

@@ -46,6 +46,8 @@ _PRODUCT_SIGS = {
     "ensemble_size": (C.c_int, [_VP]),
     "take_sc_update_count": (C.c_uint64, [_VP, C.c_int]),
     "device_count": (C.c_int, []),
+    "checkpoint_save": (C.c_int64, [_VP, C.c_char_p]),
+    "checkpoint_load": (C.c_int, [C.c_char_p, C.POINTER(_COptions), C.POINTER(_VP)]),
     "shard_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "peer_export": (C.c_int, [_VP, C.c_void_p]),
     "peer_attach": (C.c_int, [_VP, C.c_void_p, C.c_int]),
@@ -119,6 +121,33 @@ class Hierarchy(FlatHierarchy):
         """inputPtrs: device addresses (ints) of int32 [member][columns] buffers. Asynchronous."""
         ptrs = (C.c_void_p * len(inputPtrs))(*[C.c_void_p(int(p)) for p in inputPtrs])
         self._chk(self.f.step_device(self.h, ptrs, int(learnEnabled), float(reward), int(mimic)), "step_device")
+
+    def checkpointSave(self, path: str) -> int:
+        """Hierarchy::writeCheckpoint: everything, weights in their device layouts, 64-bit counts. Returns bytes written."""
+        n = int(self.f.checkpoint_save(self.h, path.encode()))
+        if n < 0:
+            raise RuntimeError(f"ogn_checkpoint_save failed: {self.f.error()}")
+        return n
+
+    @classmethod
+    def checkpointLoad(cls, path: str, inputSizes, options: "CreateOptions" = None):
+        from . import lib
+        flat = _bind_product(lib())
+        opt = options or CreateOptions()
+        co = _COptions()
+        co.device, co.device_init, co.replay_rng = opt.device, 1, int(opt.replayRng)
+        co.shard_rank, co.shard_world, co.ensemble = opt.shardRank, opt.shardWorld, 1
+        co.peer_exchange = int(opt.peerExchange)
+        h = _VP()
+        rc = flat.checkpoint_load(path.encode(), C.byref(co), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"ogn_checkpoint_load failed ({rc}): {flat.error()}")
+        obj = cls.__new__(cls)
+        FlatHierarchy.__init__(obj, flat, _handle=h)
+        obj.options, obj._cb, obj._seeds = opt, None, None
+        obj.inputSizes = [tuple(int(v) for v in s) for s in inputSizes]
+        obj.ensemble = flat.ensemble_size(h)
+        return obj
 
     def peerExport(self) -> bytes:
         """The 64-byte CUDA IPC handle of this rank's exchange arena (CreateOptions.peerExchange)."""

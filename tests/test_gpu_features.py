@@ -274,3 +274,66 @@ def test_full_size_c4_properties(product):
         top = int(np.argmax(sums))
         assert hidden[ox, oy] == top or sums[hidden[ox, oy]] >= sums[top] - 9 * 9 * 0.11, (ox, oy, hidden[ox, oy], top)
     h.close()
+
+
+def test_pyogmaneo_style_names(product, oracle, tmp_path):
+    """The pyogmaneo-style naming layer drives the same hierarchy: same predictions as the checker on the
+    sine config, save file loadable by the checker."""
+    from ogmaneo2_b200 import pyogmaneo as po
+    flat, kind = oracle
+    cfg = configs.c1_sine()
+    cs = po.ComputeSystem(seed=cfg["seed"])
+    lds = []
+    for _ in range(4):
+        ld = po.LayerDesc()
+        ld.hiddenSize = po.Int3(4, 4, 16)
+        lds.append(ld)
+    h = po.Hierarchy(cs, [po.Int3(1, 1, 32)], [po.inputTypePrediction], lds)
+    chk = FlatHierarchy(flat, cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], cfg["seed"])
+    for t in range(60):
+        v = make_inputs(cfg, t)
+        h.step(cs, [v[0].tolist()], True)
+        chk.step(v, True)
+        assert h.getPredictionCs(0) == chk.getPredictionCs(0).tolist(), f"[checker={kind}] step {t}"
+    assert h.getNumLayers() == 4 and h.getTicksPerUpdate(1) == 2
+    path = str(tmp_path / "h.ohr")
+    assert h.save(path) > 0
+    again = FlatHierarchy.load(flat, path, cfg["inputSizes"], cfg["seed"])
+    v = make_inputs(cfg, 60)
+    again.step(v, True)
+    h.step(cs, [v[0].tolist()], True)
+    assert h.getPredictionCs(0) == again.getPredictionCs(0).tolist()
+
+
+@pytest.mark.parametrize("ensemble", [1, 3])
+def test_checkpoint_round_trip(product, tmp_path, ensemble):
+    """Hierarchy::writeCheckpoint / readCheckpoint (64-bit counts, device layouts; SURVEY.md §8f-1): a hierarchy restored
+    from the file continues bit-identically to the one that wrote it — single hierarchy (2 layers, temporal horizon 2,
+    device-side init) and an ensemble."""
+    cfg = configs.c4_large(24)
+    cfg["layerDescs"].append(LayerDesc(hiddenSize=(12, 12, 16), ffRadius=2, pRadius=2, temporalHorizon=2))
+    opt = product.CreateOptions(deviceInit=True, replayRng=False, ensemble=ensemble)
+    a = product.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=5, options=opt)
+
+    def ins(t):
+        return [np.concatenate([streams.make("noisy", t, cfg["inputSizes"][0], seed=7 + k, shift=17 * k) for k in range(ensemble)])]
+    for t in range(13):
+        a.step(ins(t), True)
+    path = str(tmp_path / "h.ckpt")
+    assert a.checkpointSave(path) > 24 * 24 * 81 * 16 * 32 * 4
+    b = product.Hierarchy.checkpointLoad(path, cfg["inputSizes"], options=product.CreateOptions(replayRng=False))
+    assert b.ensemble == ensemble and b.getNumLayers() == 2
+    for t in range(13, 30):
+        a.step(ins(t), t % 5 != 0)
+        b.step(ins(t), t % 5 != 0)
+        assert np.array_equal(a.getPredictionCs(0), b.getPredictionCs(0)), f"prediction differs at step {t}"
+    if ensemble == 1:
+        d = diff_snapshots(a.snapshot(True), b.snapshot(True))
+        assert not d, d[:3]
+    else:
+        for l in range(2):
+            assert np.array_equal(a.scHiddenCs(l), b.scHiddenCs(l))
+    # a second generation checkpoint of the restored hierarchy is byte-identical to one of the original
+    pa, pb = str(tmp_path / "a2.ckpt"), str(tmp_path / "b2.ckpt")
+    a.checkpointSave(pa); b.checkpointSave(pb)
+    assert zlib.crc32(open(pa, "rb").read()) == zlib.crc32(open(pb, "rb").read())
