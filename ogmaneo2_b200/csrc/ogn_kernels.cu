@@ -874,14 +874,17 @@ static inline bool vec_geo(const ogn_rf &g) {
 }
 // OGN_KERNELS selects the step kernels: "scalar" = the generic one-cell-per-lane kernels (always used when a row does not
 // hold 8/16/32 cells); "vec1" / "vec2" = 128-bit kernels holding 8 / 16 line loads per lane in registers; "pipe4" /
-// "pipe6" = 128-bit kernels with a cp.async ring of 4 / 6 chunks per warp in shared memory. Default: see kDefaultVariant
-// (measured in profiles/README.md).
-constexpr int kDefaultVariant = 1;
+// "pipe6" = 128-bit kernels with a cp.async ring of 4 / 6 chunks per warp in shared memory. Default (unset): vec1 for
+// launches that fill the machine (bandwidth-bound: the extra registers of vec2 only cost occupancy) and vec2 for small
+// launches (latency-bound: twice the loads in flight per lane shorten the dependent chain; C2 +19 %), see
+// profiles/README.md.
+constexpr int kAutoVariant = 9;
+constexpr long long kSmallLaunchPacks = 8192; // packs x members at or below which a launch counts as latency-bound
 static int kernel_variant() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("OGN_KERNELS");
-        v = kDefaultVariant;
+        v = kAutoVariant;
         if (e && !strcmp(e, "scalar")) v = 0;
         else if (e && !strcmp(e, "vec1")) v = 1;
         else if (e && !strcmp(e, "vec2")) v = 2;
@@ -895,17 +898,20 @@ static int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
     return e ? atoi(e) : dflt;
 }
-static int vec_threads() { // threads per block of the 128-bit kernels (a multiple of 32, at most 256); OGN_VEC_THREADS overrides
-    static int v = 0;
-    if (!v) {
-        v = env_int("OGN_VEC_THREADS", kernel_variant() >= 4 ? 128 : kThreads);
-        if (v < 32 || v > kThreads || v % 32) v = kThreads;
-    }
+static int resolve_variant(long long packs) { // the variant one launch over `packs` packs (x members) uses
+    const int v = kernel_variant();
+    return v == kAutoVariant ? (packs <= kSmallLaunchPacks ? 2 : 1) : v;
+}
+static bool is_pipe(int variant) { return variant == 4 || variant == 6; }
+static int vec_threads(int variant) { // threads per block of the 128-bit kernels (a multiple of 32, at most 256); OGN_VEC_THREADS overrides
+    static int env = -1;
+    if (env < 0) env = env_int("OGN_VEC_THREADS", 0);
+    int v = env ? env : (is_pipe(variant) ? 128 : kThreads);
+    if (v < 32 || v > kThreads || v % 32) v = kThreads;
     return v;
 }
-static size_t ring_bytes(int threads) { // cp.async ring: D stages x 8 lines x 32 lanes x 16 bytes per warp
-    const int D = kernel_variant() >= 4 ? kernel_variant() : 0;
-    return (size_t)(threads / 32) * D * 4096;
+static size_t ring_bytes(int variant, int threads) { // cp.async ring: D stages x 8 lines x 32 lanes x 16 bytes per warp
+    return (size_t)(threads / 32) * (is_pipe(variant) ? variant : 0) * 4096;
 }
 
 } // extern "C"
@@ -930,8 +936,8 @@ extern "C" {
     default: { constexpr int Z = 32; CALL; } break;  \
     }
 // CALL sees the compile-time constants Z, NCH (register batch depth) and D (cp.async ring depth, 0 = registers)
-#define OGN_DISPATCH_VEC(Z_, CALL)                                                              \
-    switch (kernel_variant()) {                                                                 \
+#define OGN_DISPATCH_VEC(VARIANT_, Z_, CALL)                                                    \
+    switch (VARIANT_) {                                                                         \
     case 2: { constexpr int NCH = 2, D = 0; OGN_DISPATCH_Z(Z_, CALL); } break;                  \
     case 4: { constexpr int NCH = 1, D = 4; OGN_DISPATCH_Z(Z_, CALL); } break;                  \
     case 6: { constexpr int NCH = 1, D = 6; OGN_DISPATCH_Z(Z_, CALL); } break;                  \
@@ -950,10 +956,10 @@ int ogn_sc_forward(const ogn_fwd_args *args, int Hx, int Hy, int Hz, int x0, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (vecOk) {
-        const int vt = vec_threads();
+        const int var = resolve_variant((long long)npacks * batch), vt = vec_threads(var);
         dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
-        OGN_DISPATCH_VEC(Hz, (launch_k(vec::k_sc_forward_v<Z, NCH, D>, grid, vt, ring_bytes(vt), st, *args, Hx, Hy, x0, npacks, ppr,
-                                       hidden_cs, hidden_cs2)));
+        OGN_DISPATCH_VEC(var, Hz, (launch_k(vec::k_sc_forward_v<Z, NCH, D>, grid, vt, ring_bytes(var, vt), st, *args, Hx, Hy, x0, npacks,
+                                            ppr, hidden_cs, hidden_cs2)));
         return launch_status();
     }
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);
@@ -974,13 +980,13 @@ int ogn_sc_learn(const ogn_learn_args *args, const int *hidden_cs, const int *hi
     cudaStream_t st = (cudaStream_t)stream;
     if (ogn_sc_learn_is_split(args)) {
         const int Vz = args->geo.Vz;
-        const int vt = vec_threads();
+        const int var = resolve_variant((long long)npacks * batch * args->nvl), vt = vec_threads(var);
         dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch, (unsigned)args->nvl);
         int2 *work = (int2 *)args->work;
         unsigned *cnt = args->work_counters;
         if (phase != OGN_LEARN_UPDATE) {
-            OGN_DISPATCH_VEC(Vz, (launch_k(vec::k_sc_recon_v<Z, NCH, D>, grid, vt, ring_bytes(vt), st, *args, hidden_cs, vx0, npacks, ppr,
-                                           work, cnt)));
+            OGN_DISPATCH_VEC(var, Vz, (launch_k(vec::k_sc_recon_v<Z, NCH, D>, grid, vt, ring_bytes(var, vt), st, *args, hidden_cs, vx0,
+                                                npacks, ppr, work, cnt)));
             int e = launch_status();
             if (e || phase == OGN_LEARN_RECONSTRUCT) return e;
         }
@@ -1014,10 +1020,10 @@ int ogn_pred_step(const ogn_pred_args *args, int Hx, int Hy, int Hz, int x0, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (vecOk) {
-        const int vt = vec_threads();
+        const int var = resolve_variant((long long)npacks * batch), vt = vec_threads(var);
         dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
-        OGN_DISPATCH_VEC(Hz, (launch_k(vec::k_pred_step_v<Z, NCH, 1, D>, grid, vt, ring_bytes(vt), st, *args, Hx, Hy, x0, npacks, ppr,
-                                       learn, activate, target_cs, alpha, activations, hidden_cs)));
+        OGN_DISPATCH_VEC(var, Hz, (launch_k(vec::k_pred_step_v<Z, NCH, 1, D>, grid, vt, ring_bytes(var, vt), st, *args, Hx, Hy, x0,
+                                            npacks, ppr, learn, activate, target_cs, alpha, activations, hidden_cs)));
         return launch_status();
     }
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);

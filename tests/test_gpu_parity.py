@@ -94,7 +94,7 @@ def test_actor_more_history_samples_than_one_launch_holds(product, oracle):
 
 
 @pytest.mark.parametrize("env", [
-    {"OGN_KERNELS": "scalar"}, {"OGN_KERNELS": "vec2"}, {"OGN_KERNELS": "pipe4"}, {"OGN_KERNELS": "pipe6"},
+    {"OGN_KERNELS": "scalar"}, {"OGN_KERNELS": "vec1"}, {"OGN_KERNELS": "vec2"}, {"OGN_KERNELS": "pipe4"}, {"OGN_KERNELS": "pipe6"},
     {"OGN_GRAPHS": "0"}, {"OGN_SIDE_STREAM": "1"},
 ], ids=lambda e: "-".join(f"{k[4:].lower()}={v}" for k, v in e.items()))
 def test_every_kernel_variant_and_scheduling_mode_is_bit_exact(env):
