@@ -1,3 +1,3 @@
 cd /root/repo
-mkdir -p gpurun_out/dropin
-timeout 900 python -m pytest tests/test_dropin_cpp.py -m gpu -x -q > gpurun_out/dropin/tests.log 2>&1; tail -30 gpurun_out/dropin/tests.log
+mkdir -p gpurun_out/final5
+timeout 900 python -m pytest tests/test_gpu_features.py -m gpu -x -q -k "peer" > gpurun_out/final5/peer.log 2>&1; tail -15 gpurun_out/final5/peer.log

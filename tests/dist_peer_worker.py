@@ -45,6 +45,24 @@ def main():
         w, full = part.scWeights(l, 0), whole.scWeights(l, 0)
         own = w != 0
         assert own.any() and np.array_equal(w[own].view(np.int32), full[own].view(np.int32)), f"rank {rank}: layer {l} weights differ"
+    # per-rank checkpoint of the shard: restored into a fresh sharded hierarchy, it continues like the one that wrote it
+    import tempfile
+    path = os.path.join(tempfile.gettempdir(), f"ogn_peer_ckpt_{os.getpid()}_{rank}.ckpt")
+    part.checkpointSave(path)
+    again = og.Hierarchy.checkpointLoad(path, cfg["inputSizes"], options=og.CreateOptions(device=rank, replayRng=False, shardRank=rank,
+                                                                                       shardWorld=world, peerExchange=True))
+    os.remove(path)
+    handles = [None] * world
+    dist.all_gather_object(handles, again.peerExport())
+    again.peerAttach(handles)
+    dist.barrier()
+    for t in range(steps, steps + 6):
+        ins = make_inputs(cfg, t)
+        whole.step(ins, True)
+        again.step(ins, True)
+        a, b = again.getPredictionCs(0), whole.getPredictionCs(0)
+        assert np.array_equal(a, b), f"rank {rank}: restored shard differs at step {t}"
+    again.synchronize()
     part.synchronize()
     dist.barrier()
     print(f"rank {rank}/{world} ok")
