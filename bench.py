@@ -407,6 +407,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     h2d = sum(int(a[0].nbytes) for a in host_in)
+    if world > 1 and not ens:  # a shard uploads only the input rows its slab reads (fields of its hidden rows + its Predictor rows)
+        import ctypes as C
+        plan = (C.c_int * 6)()
+        ld0, s0 = cfg["layerDescs"][0], cfg["inputSizes"][0]
+        h.f.shard_plan(ld0.hiddenSize[0], s0[0], ld0.ffRadius, rank, world, plan)
+        x0, x1 = rank * s0[0] // world, (rank + 1) * s0[0] // world
+        h2d = (max(plan[3], x1) - min(plan[2], x0)) * s0[1] * 4
     d2h = sum(cfg["inputSizes"][i][0] * cfg["inputSizes"][i][1] * 4 * B for i in pred_idx)
 
     if rank != 0:

@@ -52,6 +52,7 @@ public:
     void getWeights(int i, std::vector<float> &out) const;
     const IntBuffer &getInputCsPrev(int i) const;
     void stateSignature(std::vector<int> &key) const; // everything that selects this layer's kernel arguments (graph cache key)
+    void hiddenRows(int &lo, int &hi) const; // hidden x rows [lo,hi) this device owns
     int copyHiddenCs(int *out) const; // getHiddenCs() straight into out (pinned staging); returns the column count
     void initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize, const std::vector<VisibleLayerDesc> &visibleLayerDescs,
                           int batch, int member);

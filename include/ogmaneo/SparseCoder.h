@@ -69,6 +69,7 @@ public:
     const int *hiddenCsDevice() const;
     // raw device state (weights in their device layouts, CSDRs, parities) of an already constructed layer of the same
     // shape: the building block of Hierarchy::writeCheckpoint / readCheckpoint
+    void visibleRows(int vli, int &lo, int &hi) const; // visible x rows [lo,hi) this device's shard of the layer reads
     int shardRank() const;
     int shardWorld() const;
     void writeDeviceState(std::ostream &os) const;

@@ -2,6 +2,7 @@
 // layer kernels on one stream (public interface: include/ogmaneo/Hierarchy.h).
 #include "LayerImpl.h"
 
+#include <algorithm>
 #include <cassert>
 #include <map>
 
@@ -200,8 +201,21 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
         r.pushFront();
         consumeKernel1(cs, (int)(r.n / m.batch));
         if (hostIn) {
-            std::memcpy(m.inPinned[i]->ptr(), hostIn[i], r.n * sizeof(int));
-            cudaCheck(cudaMemcpyAsync(r.slot(0), m.inPinned[i]->ptr(), r.n * sizeof(int), cudaMemcpyHostToDevice, ctx.stream), "input H2D");
+            // a shard only reads the input rows its slab's fields and its Predictor rows touch: copy just those
+            size_t a = 0, b = r.n;
+            if (cs.shardWorld > 1 && m.batch == 1) {
+                int lo = 0, hi = 0;
+                scLayers[0].visibleRows(i * (int)r.T, lo, hi);
+                if ((size_t)i < pLayers[0].size() && pLayers[0][i]) {
+                    int pl = 0, ph = 0;
+                    pLayers[0][i]->hiddenRows(pl, ph);
+                    lo = std::min(lo, pl); hi = std::max(hi, ph);
+                }
+                a = (size_t)lo * inputSizes[i].y; b = (size_t)hi * inputSizes[i].y;
+            }
+            std::memcpy(m.inPinned[i]->ptr() + a, hostIn[i] + a, (b - a) * sizeof(int));
+            cudaCheck(cudaMemcpyAsync(r.slot(0) + a, m.inPinned[i]->ptr() + a, (b - a) * sizeof(int), cudaMemcpyHostToDevice, ctx.stream),
+                      "input H2D");
         } else
             cudaCheck(cudaMemcpyAsync(r.slot(0), (*devIn)[i], r.n * sizeof(int), cudaMemcpyDeviceToDevice, ctx.stream), "input D2D");
     }

@@ -157,6 +157,8 @@ const IntBuffer &Predictor::getHiddenCs() const {
     return hiddenCs;
 }
 
+void Predictor::hiddenRows(int &lo, int &hi) const { lo = impl->x0; hi = impl->x1; }
+
 int Predictor::copyHiddenCs(int *out) const {
     Impl &m = *impl;
     const size_t n = m.hiddenCs.size();

@@ -315,6 +315,7 @@ void SparseCoder::setHiddenState(const IntBuffer &hc, const IntBuffer &hcPrev) {
 
 const int *SparseCoder::hiddenCsDevice() const { return impl->cs_[impl->cur].ptr(); }
 
+void SparseCoder::visibleRows(int vli, int &lo, int &hi) const { lo = impl->ws.sets[vli].vx0; hi = impl->ws.sets[vli].vx1; }
 int SparseCoder::shardRank() const { return impl->rank; }
 int SparseCoder::shardWorld() const { return impl->world; }
 
