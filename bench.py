@@ -39,7 +39,7 @@ METRIC = "hierarchy_steps_per_s_learn_on"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel at the default workload (C4 512x512), from the
 # `ncu --set full` capture summarised in profiles/README.md (filled in from the capture; None = not captured)
 TRAFFIC = {"sc_forward": 2.6998e9, "sc_learn": 1.5106e9, "pred_step": 4.3558e9, "sc_update": 1.9418e9}  # sc_update: at U = 1.3 M pairs
-PROF_PERIOD = 8
+PROF_PERIOD = 16
 UNIT = "steps/s"
 
 
