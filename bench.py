@@ -258,8 +258,8 @@ def main():
 
     # ------------------------------------------------------------------------------------------------ B200 arm
     # defaults: the step counts SURVEY.md §8d prescribes for each config (C4: 200 warm-up + 300 timed)
-    K = args.steps if args.steps is not None else {"c4": 300, "c5": 200}.get(args.workload, 2000)
-    W = args.warmup if args.warmup is not None else {"c4": 200, "c5": 50}.get(args.workload, 300)
+    K = args.steps if args.steps is not None else {"c4": 300, "c5": 300}.get(args.workload, 2000)
+    W = args.warmup if args.warmup is not None else {"c4": 200, "c5": 200}.get(args.workload, 300)
     W = max(W, 3)
     burn = args.burnin if args.burnin is not None else (max(0, 200 - W) if args.workload == "c4" else 0)
     import torch
