@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -29,8 +30,16 @@ DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
                                  ") is not compute capability 10.x; the kernels are built for sm_100a only");
     if (const char *g = std::getenv("OGN_L2_FETCH_GRANULARITY")) // experiment knob: 32 / 64 / 128 (a hint to the driver)
         cudaCheck(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g)), "cudaLimitMaxL2FetchGranularity");
-    cudaCheck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
-    cudaCheck(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate(side)");
+    // OGN_STREAM_PRIO: "main" / "side" gives that stream the device's highest priority and the other the lowest, so that
+    // when kernels of both streams have blocks pending the block scheduler always prefers the same one (experiment knob)
+    int least = 0, greatest = 0, pm = 0, ps = 0;
+    cudaCheck(cudaDeviceGetStreamPriorityRange(&least, &greatest), "cudaDeviceGetStreamPriorityRange");
+    if (const char *e = std::getenv("OGN_STREAM_PRIO")) {
+        if (!std::strcmp(e, "main")) { pm = greatest; ps = least; }
+        else if (!std::strcmp(e, "side")) { pm = least; ps = greatest; }
+    }
+    cudaCheck(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, pm), "cudaStreamCreate");
+    cudaCheck(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, ps), "cudaStreamCreate(side)");
     cudaCheck(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evLearn, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evExchange, cudaEventDisableTiming), "cudaEventCreate");
