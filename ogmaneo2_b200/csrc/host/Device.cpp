@@ -31,15 +31,19 @@ DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
     if (const char *g = std::getenv("OGN_L2_FETCH_GRANULARITY")) // experiment knob: 32 / 64 / 128 (a hint to the driver)
         cudaCheck(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g)), "cudaLimitMaxL2FetchGranularity");
     // OGN_STREAM_PRIO: "main" / "side" gives that stream the device's highest priority and the other the lowest, so that
-    // when kernels of both streams have blocks pending the block scheduler always prefers the same one (experiment knob)
-    int least = 0, greatest = 0, pm = 0, ps = 0;
-    cudaCheck(cudaDeviceGetStreamPriorityRange(&least, &greatest), "cudaDeviceGetStreamPriorityRange");
-    if (const char *e = std::getenv("OGN_STREAM_PRIO")) {
-        if (!std::strcmp(e, "main")) { pm = greatest; ps = least; }
-        else if (!std::strcmp(e, "side")) { pm = least; ps = greatest; }
+    // when kernels of both streams have blocks pending the block scheduler always prefers the same one (experiment knob,
+    // see profiles/README.md); unset: two ordinary streams
+    const char *prio = std::getenv("OGN_STREAM_PRIO");
+    if (prio && (!std::strcmp(prio, "main") || !std::strcmp(prio, "side"))) {
+        int least = 0, greatest = 0;
+        cudaCheck(cudaDeviceGetStreamPriorityRange(&least, &greatest), "cudaDeviceGetStreamPriorityRange");
+        const bool mainFirst = !std::strcmp(prio, "main");
+        cudaCheck(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, mainFirst ? greatest : least), "cudaStreamCreate");
+        cudaCheck(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, mainFirst ? least : greatest), "cudaStreamCreate(side)");
+    } else {
+        cudaCheck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        cudaCheck(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate(side)");
     }
-    cudaCheck(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, pm), "cudaStreamCreate");
-    cudaCheck(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, ps), "cudaStreamCreate(side)");
     cudaCheck(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evLearn, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evExchange, cudaEventDisableTiming), "cudaEventCreate");
