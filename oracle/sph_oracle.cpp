@@ -14,7 +14,7 @@
 // std::uniform_int_distribution<int>; SURVEY.md §8c: "do not re-implement the distributions").
 //
 // PARITY PINNING: the reference ships no tests, golden vectors or fixtures for this path, so the
-// oracle is pinned against outputs of the reference itself: tests/test_oracle_vs_reference.py steps this port and
+// oracle is pinned against outputs of the reference itself: tests/test_oracle.py steps this port and
 // oracle/_ref (the unmodified reference sources compiled here) side by side on all BASELINE configs (reduced
 // sizes) and demands bit-equal CSDRs, activations, weights, RNG state and save files; tests/golden/*.npz holds
 // reference-generated trajectories (made by tests/golden/make_golden.py) so the pin also holds where
