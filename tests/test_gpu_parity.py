@@ -130,3 +130,14 @@ def test_parameter_changes_mid_run_with_graph_replay(product, oracle):
             assert np.array_equal(a.getPredictionCs(0), b.getPredictionCs(0)), f"[checker={kind}] prediction differs at step {t}"
     d = diff_snapshots(a.snapshot(True), b.snapshot(True))
     assert not d, f"[checker={kind}] {d[:3]}"
+
+
+# Written after this round's GPU budget was spent: the shapes are pinned on the CPU (test_oracle.py) but this test has
+# not run on a B200 yet. Non-strict xfail so that an unverified test cannot turn the suite red: a pass shows as XPASS, a
+# mismatch as XFAIL with the first differing buffer in the report. Drop the marker after the first GPU run.
+@pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU budget was spent)")
+@pytest.mark.parametrize("seed", range(16))
+def test_random_shapes(product, oracle, seed):
+    """The same seeded random geometries the CPU suite pins the oracle on (tests/random_cfgs.py), on the CUDA path."""
+    from random_cfgs import random_cfg
+    _check(product, oracle, random_cfg(seed), 24, check_every=4)

@@ -144,3 +144,18 @@ def test_port_is_thread_count_independent():
         outs[-1]["rng"] = np.array([h.rngPeek()], dtype=np.uint32)
     port.set_num_threads(0)
     assert not diff_snapshots(outs[0], outs[1]) and not diff_snapshots(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_port_vs_reference_on_random_shapes(seed):
+    """Seeded random geometries (non-square, Z off the powers of two, radius 0 and radius wider than the grid, several
+    inputs, temporal horizons above the tick rate): the port must track the compiled reference bit for bit."""
+    from random_cfgs import random_cfg
+    ref = loader.ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no reference sources on this box)")
+    ref.set_num_threads(1)
+    port = loader.port()
+    port.set_num_threads(0)
+    err = run_pair(random_cfg(seed), 24, maker(port), maker(ref), check_every=4, compare_rng=True)
+    assert err is None, err
