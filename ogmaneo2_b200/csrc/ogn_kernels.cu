@@ -66,6 +66,15 @@ __device__ __forceinline__ void group_argmax(unsigned m, float &v, int &i) {
 
 template <bool kReadOnly> __device__ __forceinline__ float load_w(const float *a) { return kReadOnly ? __ldg(a) : *a; }
 
+// a / b the way the reference's x86-64 build rounds AND signals it: a column whose field is empty (radius 0 onto a much
+// smaller grid) divides 0 by 0, which SSE answers with the default NaN 0xFFC00000 while the GPU answers 0x7FFFFFFF. Every
+// NaN on this path starts at such a division (nothing else is invalid, and x86 propagates the payload it is given), so
+// mapping the quotient's NaN to the default NaN keeps even those buffers bit-identical to the reference.
+__device__ __forceinline__ float div_ref(float a, float b) {
+    const float r = a / b;
+    return r != r ? __int_as_float(0xFFC00000) : r;
+}
+
 // One pack of P y-adjacent hidden columns seen through one visible layer: the union field the pack group walks and this
 // lane's own column's y-range inside it.
 struct PackCtx {
@@ -302,7 +311,7 @@ k_sc_learn(const __grid_constant__ ogn_learn_args A, const int *__restrict__ hcs
                 }
             }
         }
-        sum = sum / (float)ncov;
+        sum = div_ref(sum, (float)ncov);
         if (act) recon[vc] = sum;
         if (vc0 == 0) myRecon = sum;
         // chunk arg-max: element 0 of the whole column is always taken first, NaN elsewhere never wins
@@ -426,7 +435,7 @@ k_pred_step(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int Hz, int
             sum += gather_pack<G, false>(gm, gl, w, cs, c, rf.Vy, rf.Vz, P * Hz);
             count += c.dn * (c.nslotsU / max(c.nyU, 1)); // own field: nx * ny
         }
-        sum = sum / (float)count;
+        sum = div_ref(sum, (float)count);
         if (act) acts[col * Hz + hc] = sum;
         float v = (act && sum > -999999.0f) ? sum : (act ? -999999.0f : -INFINITY);
         int i = act ? hc : 0x7fffffff;
@@ -526,7 +535,7 @@ __device__ __forceinline__ float actor_action_acts(unsigned gm, unsigned sm, int
             const float *w = A.vl[v].wa + c.blk + p * Hz + hcl;
             sum += gather_pack<G, false>(gm, gl, w, csv[v], c, rf.Vy, rf.Vz, P * Hz);
         }
-        sum = sum / (float)count;
+        sum = div_ref(sum, (float)count);
         if (hc0 == 0) mine = sum;
         if (act && Hz > G) acts[hc] = sum;
     }
@@ -579,7 +588,7 @@ k_actor_forward(const __grid_constant__ ogn_actor_args A, int Hx, int Hy, int Hz
     for (int v = 0; v < A.nvl; ++v) csv[v] = A.vl[v].cs;
     int count;
     const float value = actor_value<G>(sm, hl, colValid, A, csv, ox, oyc, &count);
-    if (hl == 0 && colValid) hiddenValues[col] = value / (float)count;
+    if (hl == 0 && colValid) hiddenValues[col] = div_ref(value, (float)count);
     float *acts = hiddenActs + (long long)col * Hz;
     const float mine = actor_action_acts<G>(gm, sm, gl, p, hl, colValid, A, csv, ox, q, Hz, count, acts);
     if (!colValid) return;
@@ -637,7 +646,7 @@ k_actor_learn(const __grid_constant__ ogn_actor_args A, const __grid_constant__ 
         const float newValue = S.q + S.g * hiddenValues[col];
         int count;
         float value = actor_value<G>(sm, hl, colValid, A, S.cs, ox, oyc, &count);
-        value = value / (float)count;
+        value = div_ref(value, (float)count);
         const float tdErrorValue = newValue - value;
         const float deltaValue = alpha * tdErrorValue;
         for (int v = 0; v < A.nvl; ++v) value_row_delta<G>(hl, colValid, A.geo[A.vl[v].geo_v], A.vl[v].wv, S.cs[v], ox, oyc, deltaValue);

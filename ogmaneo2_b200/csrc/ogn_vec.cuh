@@ -379,7 +379,7 @@ k_pred_step_v(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int x0, i
         count += c.dn * (c.nslotsU / max(c.nyU, 1)); // own field: nx * ny
     }
     const float cnt = (float)count;
-    sum.x = sum.x / cnt; sum.y = sum.y / cnt; sum.z = sum.z / cnt; sum.w = sum.w / cnt;
+    sum.x = div_ref(sum.x, cnt); sum.y = div_ref(sum.y, cnt); sum.z = div_ref(sum.z, cnt); sum.w = div_ref(sum.w, cnt);
     if (id.colValid) st_plain(act4, sum);
     const int best = column_argmax_fwd<Z>(om, id.hz0, sum);
     if (id.hz0 == 0 && id.colValid) hiddenCs[col] = best;
@@ -529,7 +529,7 @@ k_sc_recon_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ h
         }
     }
     const float cnt = (float)ncov;
-    sum.x = sum.x / cnt; sum.y = sum.y / cnt; sum.z = sum.z / cnt; sum.w = sum.w / cnt;
+    sum.x = div_ref(sum.x, cnt); sum.y = div_ref(sum.y, cnt); sum.z = div_ref(sum.z, cnt); sum.w = div_ref(sum.w, cnt);
     if (colValid) st_plain(vl.recon + vcol * Z + vc0, sum);
 
     // arg-max with the reference's `sum > max || maxIndex == -1` rule (SparseCoder.cpp:60-66): element 0 is always taken

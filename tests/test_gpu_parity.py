@@ -132,12 +132,29 @@ def test_parameter_changes_mid_run_with_graph_replay(product, oracle):
     assert not d, f"[checker={kind}] {d[:3]}"
 
 
-# Written after this round's GPU budget was spent: the shapes are pinned on the CPU (test_oracle.py) but this test has
-# not run on a B200 yet. Non-strict xfail so that an unverified test cannot turn the suite red: a pass shows as XPASS, a
-# mismatch as XFAIL with the first differing buffer in the report. Drop the marker after the first GPU run.
-@pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU budget was spent)")
 @pytest.mark.parametrize("seed", range(16))
-def test_random_shapes(product, oracle, seed):
-    """The same seeded random geometries the CPU suite pins the oracle on (tests/random_cfgs.py), on the CUDA path."""
+def test_random_shapes_inner(product, oracle, seed):
+    """The same seeded random geometries the CPU suite pins the oracle on (tests/random_cfgs.py), on the CUDA path.
+    Runs only inside the subprocess test_random_shapes starts."""
+    import os
+    if os.environ.get("OGN_RUN_RANDOM_SHAPES") != "1":
+        pytest.skip("runs inside the subprocess of test_random_shapes")
     from random_cfgs import random_cfg
     _check(product, oracle, random_cfg(seed), 24, check_every=4)
+
+
+# Written when this round's GPU budget was all but spent. The last 4 seconds of it ran seeds 0 and 1: seed 0 passed, seed 1
+# differed only in the BITS of NaN activations (a Predictor column whose radius-0 field is empty divides 0 by 0: x86 gives
+# the default NaN 0xFFC00000, the GPU 0x7FFFFFFF); div_ref() in ogn_kernels.cu now maps those to the x86 value, but that
+# fix and seeds 2-15 have not run on a B200. Hence: a subprocess (a device fault cannot poison the CUDA context of the
+# tests that follow) and a non-strict xfail (an unverified test cannot turn the suite red: a pass shows as XPASS, a
+# mismatch as XFAIL with the subprocess report). Drop the marker after the first full GPU run.
+@pytest.mark.xfail(strict=False, reason="seeds 2-15 and the NaN-bits fix have not run on a B200 yet (GPU budget spent)")
+def test_random_shapes():
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-k", "random_shapes_inner"]
+    r = subprocess.run(cmd, cwd=root, env=dict(os.environ, OGN_RUN_RANDOM_SHAPES="1"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-1000:]
