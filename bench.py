@@ -38,9 +38,24 @@ from ogmaneo2_b200.flat_api import FlatHierarchy, InputType  # noqa: E402
 METRIC = "hierarchy_steps_per_s_learn_on"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel at the default workload (C4 512x512), from the
 # `ncu --set full` capture summarised in profiles/README.md (filled in from the capture; None = not captured)
-TRAFFIC = {"sc_forward": 2.6998e9, "sc_learn": 1.5106e9, "pred_step": 4.3558e9, "sc_update": 1.9418e9}  # sc_update: at U = 1.3 M pairs
-PROF_PERIOD = 16
+TRAFFIC_CSV = os.path.join(ROOT, "profiles", "ncu_c4_512_traffic.csv")
 UNIT = "steps/s"
+
+
+def load_traffic():
+    """kernel kind -> DRAM bytes per launch at the default workload, read from the committed summary of the latest
+    `ncu --set full` capture (profiles/ncu_c4_512_traffic.csv: kind,kernel,dram_bytes_read,dram_bytes_write,source)."""
+    out, src = {}, None
+    try:
+        with open(TRAFFIC_CSV) as f:
+            for line in f:
+                p = [x.strip() for x in line.split(",")]
+                if len(p) >= 5 and p[0] != "kind" and not p[0].startswith("#"):
+                    out[p[0]] = float(p[2]) + float(p[3])
+                    src = p[4]
+    except OSError:
+        pass
+    return out, src
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -183,8 +198,8 @@ class _DevArray:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def time_cpu(cfg_sample, steps, warmup, full_cols, budget_s=25.0):
-    """The reference's CPU implementation on a bounded sample; returns (full-workload steps/s, info dict)."""
+def time_cpu(cfg_sample, steps, warmup, full_cols, budget_s=25.0, want_trace=False):
+    """The reference's CPU implementation on a bounded sample; returns (full-workload steps/s, info dict[, trace])."""
     from oracle import loader
     flat, kind = loader.best()
     cores = os.cpu_count() or 1
@@ -195,24 +210,107 @@ def time_cpu(cfg_sample, steps, warmup, full_cols, budget_s=25.0):
     h = FlatHierarchy(flat, cfg_sample["inputSizes"], cfg_sample["inputTypes"], cfg_sample["layerDescs"], cfg_sample["seed"])
     t_init = time.perf_counter() - t0
     ins = lambda t: [streams.make(k if k != "action" else "iid", t, s) for s, k in zip(cfg_sample["inputSizes"], cfg_sample["streams"])]
+    pred_input = next((i for i, t in enumerate(cfg_sample["inputTypes"]) if t == InputType.prediction), None)
+    trace = {"inputs": ins, "pred": [], "pred_input": pred_input}
+    keep = want_trace and pred_input is not None and not has_actor
     for t in range(warmup):
         h.step(ins(t), True)
+        if keep:
+            trace["pred"].append(h.getPredictionCs(pred_input))
     done, t0 = 0, time.perf_counter()
     pre = [ins(warmup + t) for t in range(steps)]
+    untimed = 0.0
     t0 = time.perf_counter()
     for t in range(steps):
         h.step(pre[t], True)
         done += 1
-        if time.perf_counter() - t0 > budget_s:
+        if keep:  # reading the prediction back is not part of the timed work
+            u0 = time.perf_counter()
+            trace["pred"].append(h.getPredictionCs(pred_input))
+            untimed += time.perf_counter() - u0
+        if time.perf_counter() - t0 - untimed > budget_s:
             break
-    dt = time.perf_counter() - t0
+    dt = time.perf_counter() - t0 - untimed
+    if keep:
+        trace["hidden0"] = h.scHiddenCs(0)
     sample_cols = sum(ld.hiddenSize[0] * ld.hiddenSize[1] for ld in cfg_sample["layerDescs"][:1])
     sample_sps = done / dt
     scale = sample_cols / full_cols  # column-steps/s is the size-independent rate for the single-layer config
     h.close()
     info = {"kind": kind, "cores": threads, "sample": f"{cfg_sample['name']}: {done} steps in {dt:.2f}s after {warmup} warm-up "
             f"(init {t_init:.1f}s), scaled by hidden columns {sample_cols}/{full_cols}", "sample_steps_per_s": sample_sps}
+    if want_trace:
+        return sample_sps * scale, info, (trace if keep else None)
     return sample_sps * scale, info
+
+
+def state_hash(h, cfg, pred_idx, rank, world, dist, ens):
+    """crc32 over the prediction CSDRs, every SparseCoder's hidden CSDR and a sample of weight columns (SparseCoder and
+    Predictor, 8 columns per layer spread over the x-slabs, fetched from whichever rank stores them), taken after the last
+    step of the run. The run is deterministic, so the hash must not depend on --gpus: N = 8 equal to N = 1 is the
+    sharded-equals-unsharded check of SURVEY.md 8e on the full-size layer. Ensembles hash rank 0's members."""
+    import ctypes as C
+    import zlib
+    lib = h.f.lib
+    lib.ogn_debug_column_weights.restype = C.c_int64
+    lib.ogn_debug_column_weights.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int64]
+    crc = 0
+    for i in pred_idx:
+        crc = zlib.crc32(np.ascontiguousarray(h.getPredictionCs(i)).tobytes(), crc)
+    L = len(cfg["layerDescs"])
+    for l in range(L):
+        crc = zlib.crc32(np.ascontiguousarray(h.scHiddenCs(l)).tobytes(), crc)
+    mine = {}
+    if not ens:
+        for l, ld in enumerate(cfg["layerDescs"]):
+            Hx, Hy = ld.hiddenSize[0], ld.hiddenSize[1]
+            # (kind, layer, grid x extent, grid y extent): the SparseCoder, and predictor 0 of the layer (layer 0: first
+            # prediction input; its hidden grid is the input grid)
+            targets = [(0, l, Hx, Hy)]
+            if l == 0 and pred_idx and cfg["inputTypes"][pred_idx[0]] == InputType.prediction and pred_idx[0] == 0:
+                targets.append((1, l, cfg["inputSizes"][0][0], cfg["inputSizes"][0][1]))
+            elif l > 0:
+                targets.append((1, l, cfg["layerDescs"][l - 1].hiddenSize[0], cfg["layerDescs"][l - 1].hiddenSize[1]))
+            for kind, ll, gx, gy in targets:
+                for k in range(8):
+                    ox, oy = min(gx - 1, (2 * k + 1) * gx // 16), (37 * k + 5) % gy
+                    owner = ox * world // gx if world > 1 and gx % world == 0 else 0
+                    if owner != rank:
+                        continue
+                    n = lib.ogn_debug_column_weights(h.h, kind, ll, 0, ox, oy, None, 0)
+                    if n <= 0:
+                        raise RuntimeError(f"state_hash: column weights unavailable: {h.f.error()}")
+                    buf = np.empty(n, dtype=np.float32)
+                    lib.ogn_debug_column_weights(h.h, kind, ll, 0, ox, oy, buf.ctypes.data_as(C.POINTER(C.c_float)), n)
+                    mine[(kind, ll, k)] = zlib.crc32(buf.tobytes())
+    allw = [mine]
+    if dist is not None and not ens:
+        allw = [None] * world
+        dist.all_gather_object(allw, mine)
+    merged = {}
+    for d in allw:
+        merged.update(d)
+    for key in sorted(merged):
+        crc = zlib.crc32(np.array([key[0], key[1], key[2], merged[key]], dtype=np.int64).tobytes(), crc)
+    return f"{crc:08x}", len(merged)
+
+
+def parity_sample(og, cfg_sample, ref_trace, device):
+    """The CPU sample the cpu_baseline leg just timed, replayed on the GPU at the SAME size from the same seed and inputs
+    (std::mt19937 init in the reference's order): every step's prediction CSDR and the final hidden CSDR must be bit-equal."""
+    opt = og.CreateOptions(device=device, deviceInit=False, replayRng=False)
+    g = og.Hierarchy(cfg_sample["inputSizes"], cfg_sample["inputTypes"], cfg_sample["layerDescs"], seed=cfg_sample["seed"], options=opt)
+    ok, first_bad = True, None
+    for t, want in enumerate(ref_trace["pred"]):
+        g.step(ref_trace["inputs"](t), True)
+        if not np.array_equal(g.getPredictionCs(ref_trace["pred_input"]), want):
+            ok, first_bad = False, t
+            break
+    if ok and not np.array_equal(g.scHiddenCs(0), ref_trace["hidden0"]):
+        ok, first_bad = False, "final hidden CSDR"
+    g.close()
+    return {"config": cfg_sample["name"], "steps_compared": len(ref_trace["pred"]), "bit_identical": ok, "first_difference": first_bad,
+            "what": "prediction CSDR after every step + final layer-0 hidden CSDR, GPU vs the CPU run that was just timed"}
 
 
 def main():
@@ -250,6 +348,12 @@ def main():
         value, info = time_cpu(cfg["sample"], max(K, 40) if args.workload == "c4" else K, W, full_cols, budget_s=60.0)
         info["value"] = value
         info["unit"] = UNIT
+        same = cfg["sample"]["name"] == cfg["name"]
+        config["same_config"] = same
+        config["extrapolated"] = not same
+        if not same:  # the reference cannot construct the full size: say what actually ran
+            config["workload"] = (f"{cfg['sample']['name']} sample of [{cfg['desc']}]: the reference ran {info['sample']}; value = "
+                                  "sample steps/s x sample hidden columns / full hidden columns")
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
                           "warmup": W, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": info,
@@ -357,7 +461,9 @@ def main():
     barrier()
     for l in range(len(cfg["layerDescs"])):
         h.takeSCUpdateCount(l)
-    # per-kernel CUDA events on every PROF_PERIOD-th step of the timed region (every step would cost ~8% of a sharded step)
+    # per-kernel CUDA events on every PROF_PERIOD-th step of the timed region (every step would cost ~8% of a sharded step):
+    # at least 16 bracketed steps whatever K is
+    PROF_PERIOD = max(1, K // 16)
     h.profileEnable(os.environ.get("OGN_BENCH_NOPROF") != "1", period=PROF_PERIOD)
     if peer:
         h.peerTakeWaitNs()
@@ -375,7 +481,8 @@ def main():
     wall1 = time.time()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop(wall0, wall1) if clocks else None
-    prof = h.profileRead()
+    prof_t = h.profileRead(timed=True)
+    prof = {k: (v[0] * (v[1] / v[2]) if v[2] else 0.0, v[1]) for k, v in prof_t.items()}
     h.profileEnable(False)
     upd = [h.takeSCUpdateCount(l) for l in range(len(cfg["layerDescs"]))]
     ranks_info = None
@@ -415,6 +522,10 @@ def main():
         x0, x1 = rank * s0[0] // world, (rank + 1) * s0[0] // world
         h2d = (max(plan[3], x1) - min(plan[2], x0)) * s0[1] * 4
     d2h = sum(cfg["inputSizes"][i][0] * cfg["inputSizes"][i][1] * 4 * B for i in pred_idx)
+    try:
+        shash, scols = state_hash(h, cfg, pred_idx, rank, world, dist, ens)
+    except Exception as e:  # never take the timing down with it
+        shash, scols = f"unavailable: {e!r}", 0
 
     if rank != 0:
         if dist is not None:
@@ -429,6 +540,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic, traffic_src = load_traffic()
     sites = bytes_per_launch(cfg)
     counts = tick_counts(cfg, burn + W + K)[burn + W:].sum(axis=0)  # updates per layer inside the timed region
     alg = {}
@@ -443,12 +555,15 @@ def main():
         alg["sc_update"] = upd_bytes
     elif "sc_learn" in alg:
         alg["sc_learn"] += upd_bytes
+    if prof.get("hier_small", (0.0, 0))[1] > 0:  # the whole step ran as ONE kernel: its bytes are the step's bytes
+        alg = {"hier_small": sum(alg.values())}
     kernels = {}
     for kind, (kms, n) in prof.items():
         if n == 0:
             continue
         ab = alg.get(kind, 0.0)
-        kernels[kind] = {"launches": int(n), "ms_per_launch": kms / n, "alg_bytes_per_launch": ab / n if ab else None,
+        kernels[kind] = {"launches": int(n), "timed_launches": int(prof_t[kind][2]), "ms_per_launch": kms / n,
+                         "alg_bytes_per_launch": ab / n if ab else None,
                          "achieved_gbs": (ab / n) / (kms / n * 1e-3) / 1e9 if ab and kms > 0 else None,
                          "share_of_step": kms / ms}
     cand = [k for k in kernels if kernels[k]["achieved_gbs"]]
@@ -456,8 +571,9 @@ def main():
     total_alg = sum(alg.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["achieved_gbs"] / peak if dom else None,
-                "traffic": TRAFFIC.get(dom) if args.workload == "c4" and world == 1 and not args.size else None,
-                "traffic_source": "profiles/r1_ncu_c4_512_summary.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                "traffic": traffic.get(dom) if args.workload == "c4" and world == 1 and not args.size else None,
+                "traffic_source": (f"profiles/ncu_c4_512_traffic.csv <- {traffic_src} (ncu --set full, dram__bytes_read.sum + "
+                                   "dram__bytes_write.sum per launch)") if traffic else None,
                 "peak_source": peak_src,
                 "step_achieved_gbs": total_alg / (ms * 1e-3) / 1e9, "step_frac": total_alg / (ms * 1e-3) / 1e9 / peak,
                 "alg_bytes_per_step_per_gpu": total_alg / K, "kernels": kernels,
@@ -466,9 +582,14 @@ def main():
     cpu = None
     if not args.no_cpu and args.gpus == 1:
         try:
-            v, info = time_cpu(cfg["sample"], 60 if args.workload == "c4" else 10, 1, full_cols, budget_s=12.0)
+            v, info, trace = time_cpu(cfg["sample"], 60 if args.workload == "c4" else 10, 1, full_cols, budget_s=12.0, want_trace=True)
             info["value"], info["unit"] = v, UNIT
             cpu = info
+            if trace is not None and not ens:
+                try:
+                    cpu["gpu_parity_on_sample"] = parity_sample(og, cfg["sample"], trace, local_rank)
+                except Exception as e:
+                    cpu["gpu_parity_on_sample"] = {"bit_identical": None, "error": repr(e)}
         except Exception as e:  # the baseline must never take the GPU result down with it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
 
@@ -480,12 +601,16 @@ def main():
                    else "weights exceed L2" if args.workload == "c2" else "L2-resident (latency-bound config)",
                    "init": "device counter-hash" if cfg["device_init"] else "std::mt19937 in reference order",
                    "burn_in_steps": burn,
-                   "kernel_timing": f"CUDA events around every kernel launch of every {PROF_PERIOD}th step of the timed region"})
+                   "kernel_timing": f"CUDA events around every kernel launch of every {PROF_PERIOD}th step of the timed region "
+                                    "(timed_launches per kernel in roofline.kernels)"})
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
            "higher_is_better": True, "scaling": "weak" if ens else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": config, "roofline": roofline, "cpu_baseline": cpu,
            "e2e": {"value": Ke / e2e_s * (B * world if ens else 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
            "gpu_launches": int(sum(n for _, n in prof.values())), "clocks": clk,
+           "state_hash": {"crc32": shash, "weight_columns": scols, "after_steps": burn + W + K + Ke,
+                          "covers": "prediction CSDRs, SparseCoder hidden CSDRs, 8 SparseCoder + 8 Predictor weight columns per layer; "
+                                    "independent of --gpus for the same --steps/--warmup"},
            "ranks": ranks_info, "host_enqueue_ms_per_step": host_enqueue_ms,
            "column_steps_per_s": value * sum(ld.hiddenSize[0] * ld.hiddenSize[1] * c for ld, c in zip(cfg["layerDescs"], counts)) / K}
     print(json.dumps(out))

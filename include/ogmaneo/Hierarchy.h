@@ -116,6 +116,7 @@ private:
 
     void initImpl(ComputeSystem &cs, const std::vector<Int3> &inputSizes, const std::vector<InputType> &inputTypes,
                   const std::vector<LayerDesc> &layerDescs, int batch, int member);
+    bool smallEligible(ComputeSystem &cs);
     void stepImpl(ComputeSystem &cs, const int *const *hostIn, const std::vector<const int *> *devIn,
                   bool learnEnabled, float reward, bool mimic);
 };

@@ -51,6 +51,9 @@ public:
     const FloatBuffer &getHiddenActivations() const; // private in the reference (Predictor.h:42)
     void getWeights(int i, std::vector<float> &out) const;
     const IntBuffer &getInputCsPrev(int i) const;
+    // weights of ONE hidden column (ox, oy) towards visible layer i in the reference's CSR order [hz][slot][vz]
+    void getColumnWeights(int i, int ox, int oy, std::vector<float> &out) const;
+    int smallUnits() const; // see SparseCoder::smallUnits
     void stateSignature(std::vector<int> &key) const; // everything that selects this layer's kernel arguments (graph cache key)
     void hiddenRows(int &lo, int &hi) const; // hidden x rows [lo,hi) this device owns
     int copyHiddenCs(int *out) const; // getHiddenCs() straight into out (pinned staging); returns the column count

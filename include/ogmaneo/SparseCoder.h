@@ -64,6 +64,9 @@ public:
                           int batch, int member);
     // step() on inputs that already live in device memory (int32 [member][columns]); copyOut (optional) also receives
     // the new hiddenCs. Asynchronous on cs' stream.
+    // work units per member the largest phase of this layer needs in the single-launch small-hierarchy step (one per pack of
+    // the forward pass / per (visible layer, pack) of the reconstruction), or -1 if some phase has no 128-bit kernel path
+    int smallUnits() const;
     void stateSignature(std::vector<int> &key) const; // everything that selects this layer's kernel arguments (graph cache key)
     void stepDevice(ComputeSystem &cs, const int *const *inputCsDevice, bool learnEnabled, int *copyOut);
     const int *hiddenCsDevice() const;

@@ -103,6 +103,12 @@ typedef struct ogn_hierarchy_desc {
        save returns bytes written or -1. load creates a new handle whose ComputeSystem rng is seeded with seed. */ \
     int64_t P##save(void *h, const char *path);                                                                    \
     int P##load(const char *path, uint32_t seed, void **out);                                                      \
+    /* Hierarchy::getState / setState, Hierarchy.cpp:434-493 (struct State, Hierarchy.h:26-36): a snapshot of every  \
+       CSDR of the hierarchy (hidden states, predictor outputs and previous inputs, history rings, ticks, updates;  \
+       no weights) as an opaque object owned by the caller; set_state rewinds the hierarchy to it. */              \
+    int P##get_state(void *h, void **state_out);                                                                   \
+    int P##set_state(void *h, const void *state);                                                                  \
+    void P##free_state(void *state);                                                                               \
     /* Next raw output of a COPY of cs.rng (ComputeSystem.h:24): lets tests compare RNG consumption without        \
        disturbing it. */                                                                                           \
     uint32_t P##rng_peek(void *h);

@@ -50,6 +50,8 @@ typedef struct ogn_rf {
     const int *rloy, *rhiy;   /* [Vy] */
     int max_nx, max_nyf;      /* largest nx[] / nyf[] entry: bounds the slot descriptors of the 128-bit kernels */
     int max_cov;              /* largest number of hidden columns covering one visible column */
+    int tma_ok;               /* 1: CSDR windows of this pairing can be staged by bulk copies (Vy % 4 == 0, every union field
+                                 non-empty, field starts and ends non-decreasing along y) */
 } ogn_rf;
 
 /* ---- per-launch descriptors, all passed BY VALUE (kernel parameter space): a launch never chases a descriptor
@@ -141,7 +143,70 @@ typedef struct ogn_actor_batch {
     int n;
 } ogn_actor_batch;
 
+/* One phase of the single-launch small-hierarchy step (ogn_hier_step_small): the arguments one of the launchers below
+ * would have been given, plus the scheduling flags of the in-kernel phase loop. An array of these lives in DEVICE memory
+ * (the union makes an element ~1.8 KB; a step of a 4-layer hierarchy has at most ~20 phases). */
+#define OGN_PHASE_SC_FORWARD 0
+#define OGN_PHASE_SC_RECON 1
+#define OGN_PHASE_SC_UPDATE 2
+#define OGN_PHASE_PRED 3
+#define OGN_SMALL_MAX_LISTS 30  /* work lists (reconstruction/update pairs) per step */
+#define OGN_SMALL_COUNTERS (2 + OGN_SMALL_MAX_LISTS) /* per member: barrier {arrivals, generation} + list fills */
+typedef struct ogn_small_phase {
+    int kind;                 /* OGN_PHASE_* */
+    int z;                    /* row width of the phase's 128-bit kernels: Hz (forward, Predictor) or Vz (reconstruction, update) */
+    int reserved;
+    int barrierAfter;         /* 1: the blocks of a member meet before the next phase starts */
+    int counter;              /* work-list slot (reconstruction / update pairs share one) */
+    int Hx, Hy;               /* grid the packs tile: hidden grid (forward, Predictor), visible grid (reconstruction) */
+    int npacks, ppr;          /* packs per member and per grid row */
+    int learn, activate;      /* Predictor */
+    int updVer, chunks;       /* update: kernel version (1 | 2) and work units per list entry */
+    float alpha;
+    int *out0, *out1;         /* forward: hiddenCs + optional copy; Predictor: hiddenCs */
+    const int *target;        /* Predictor learn target */
+    float *acts;              /* Predictor activations */
+    const int *hcs, *hcsPrev; /* reconstruction / update: SparseCoder hiddenCs and hiddenCsPrev */
+    void *work;               /* work list base; member m uses [m * workStride, (m + 1) * workStride) entries of 8 bytes */
+    int64_t workStride;
+    unsigned long long *updCount;
+    union {
+        ogn_fwd_args fwd;
+        ogn_learn_args learn;
+        ogn_pred_args pred;
+    } u;
+} ogn_small_phase;
+
 const char *ogn_cuda_error_string(int code);
+
+/* 1 if rows of z cells / this geometry have a 128-bit kernel path (rows of 8, 16 or 32 cells; slot descriptors fit their bit
+ * fields): what a caller planning a single-launch step needs to know. */
+int ogn_vec_row_ok(int z);
+int ogn_vec_geo_ok(const ogn_rf *rf_host);
+/* update kernel version the library would use for this geometry (2 needs Hz % 8 == 0; OGN_SC_UPDATE=1|2 overrides), and
+ * the work units per list entry for that version */
+int ogn_sc_update_version(const ogn_learn_args *args_host);
+int ogn_sc_update_chunks(const ogn_learn_args *args_host, int version);
+
+/* The whole step of a small hierarchy in ONE launch (SURVEY.md 8(b2) ogn_hier_step_small; replaces the ~54 runKernelN
+ * fork/joins of Hierarchy::step, Hierarchy.cpp:219-284, Helpers.cpp:15-72): the phases (device array) run in order
+ * inside one kernel, the blocks of a member meeting at a barrier wherever barrierAfter is set. wide = 1: one warp per pack
+ * (latency mapping: a single small hierarchy), 0: one octet per pack (bandwidth mapping: ensembles). grid =
+ * (blocks_per_member, members); blocks_per_member > 1 launches cooperatively (all blocks co-resident) and fails with
+ * cudaErrorCooperativeLaunchTooLarge if they do not fit. counters: members x OGN_SMALL_COUNTERS zero-initialised words,
+ * left at zero. max_blocks_per_member(threads) tells how many blocks of `threads` threads can be co-resident. */
+/* K1 inside the same launch (Hierarchy.cpp:205-212): before the first phase every member copies count[i] ints of src[i]
+ * (device-resident input CSDR, [member][count]) to dst[i] (the front slot of the layer-0 history ring). */
+#define OGN_SMALL_MAX_INPUTS 4
+typedef struct ogn_small_inputs {
+    const int *src[OGN_SMALL_MAX_INPUTS];
+    int *dst[OGN_SMALL_MAX_INPUTS];
+    int count[OGN_SMALL_MAX_INPUTS];
+    int n;
+} ogn_small_inputs;
+int ogn_hier_step_small(const ogn_small_phase *phases_dev, int nphases, const ogn_small_inputs *inputs_host, int members,
+                        int blocks_per_member, int threads, int wide, unsigned *counters_dev, void *stream);
+int ogn_hier_small_max_blocks(int threads);
 
 /* K2 — SparseCoder::forward (SparseCoder.cpp:13-43) + multiplyOHVs (SparseMatrix.cpp:260-276) over hidden x in
  * [x0,x1): gather-sum and first-max arg-max. hidden_cs2 (optional) receives a second copy: the next layer's history
@@ -214,6 +279,11 @@ int ogn_weights_init_hash(const ogn_wset *wset_host, const ogn_rf *rf_host, int 
 /* Number of elements where the F and R copies of a SparseCoder weight set disagree (debug / tests). */
 int ogn_weights_fr_mismatch(const ogn_wset *wset_host, const ogn_rf *rf_host, int member, unsigned long long *count_dev,
                             void *stream);
+
+/* Launch counts per (kernel, variant) since the library was loaded: out[k*8 + c], k = 0 SparseCoder forward, 1 SparseCoder
+ * reconstruction, 2 Predictor step; c = 0 generic one-cell-per-lane, 1 vec1, 2 vec2, 3 pipe4, 4 pipe6, 5 tma, 6 wide, 7 unused.
+ * Tests use it to assert which kernel the default selector ran at a given size. */
+void ogn_debug_variant_launches(long long out[24]);
 
 /* Device replays of glibc expf/tanhf (csrc/ogn_libm.h), exposed for tests: out[i] = f(in[i]). */
 int ogn_test_expf(const float *in, float *out, int64_t n, void *stream);

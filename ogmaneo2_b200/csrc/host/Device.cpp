@@ -50,6 +50,9 @@ DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
     cudaCheck(cudaEventCreateWithFlags(&evPredLearn, cudaEventDisableTiming), "cudaEventCreate");
     if (const char *e = std::getenv("OGN_SIDE_STREAM")) useSide = std::atoi(e) != 0; // 0: everything on one stream
     if (const char *e = std::getenv("OGN_GRAPHS")) graphs = std::atoi(e) != 0;
+    if (const char *e = std::getenv("OGN_SMALL_KERNEL")) small = std::atoi(e) != 0;
+    if (std::getenv("OGN_KERNELS")) small = false; // a forced kernel variant means the per-phase launches are under test
+    if (const char *e = std::getenv("OGN_SMALL_MAX_UNITS")) smallMaxUnits = std::atoi(e);
 }
 
 void DeviceContext::forkSide() {
@@ -259,6 +262,14 @@ void Geometry::build(const Int3 &hidden, const Int3 &visible, int r) {
     for (int i = 0; i < Vx; i++) mcx = std::max(mcx, rhix[i] - rlox[i] + 1);
     for (int i = 0; i < Vy; i++) mcy = std::max(mcy, rhiy[i] - rloy[i] + 1);
     host.max_cov = std::max(mcx, 0) * std::max(mcy, 0);
+    bool tma = Vy % 4 == 0 && !nyf.empty();
+    for (size_t q = 0; q < nyf.size() && tma; q++) {
+        if (nyf[q] <= 0) tma = false;
+        if (q > 0 && (loyf[q] < loyf[q - 1] || loyf[q] + nyf[q] < loyf[q - 1] + nyf[q - 1])) tma = false;
+    }
+    for (int o = 0; o < Hx && tma; o++)
+        if (nx[o] <= 0) tma = false;
+    host.tma_ok = tma ? 1 : 0;
 }
 
 std::shared_ptr<Geometry> Geometry::get(const Int3 &hidden, const Int3 &visible, int radius) {

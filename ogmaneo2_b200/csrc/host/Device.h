@@ -24,7 +24,19 @@ namespace detail {
 void cudaCheck(cudaError_t e, const char *what);
 inline void kernelCheck(int code, const char *what) { cudaCheck((cudaError_t)code, what); }
 
-enum KernelKind { kScForward = 0, kScLearn = 1, kPredStep = 2, kActorForward = 3, kActorLearn = 4, kScUpdate = 5, kKernelKinds = 6 };
+enum KernelKind { kScForward = 0, kScLearn = 1, kPredStep = 2, kActorForward = 3, kActorLearn = 4, kScUpdate = 5, kHierSmall = 6, kKernelKinds = 7 };
+
+// Phases of one Hierarchy::step recorded instead of launched (DeviceContext::collect): the single-launch small-hierarchy
+// kernel runs them from a device-resident array (ogn_hier_step_small). layer / role let Hierarchy::step order them into
+// barrier levels.
+struct SmallPlan {
+    struct Node { ogn_small_phase ph; int layer; };
+    std::vector<Node> nodes;
+    int curLayer = 0;
+    int lists = 0;      // work lists handed out so far
+    bool ok = true;     // false: some phase has no 128-bit path (the plan must not be launched)
+    void add(const ogn_small_phase &p) { nodes.push_back(Node{p, curLayer}); }
+};
 
 // Peer-memory exchange of sharded CSDRs (one process per GPU on one NVLink / NVSwitch node). Every CSDR buffer a
 // sharded layer exchanges is carved out of ONE arena per device, in construction order, so it sits at the same offset on
@@ -69,6 +81,10 @@ struct DeviceContext {
     // graphs: Hierarchy::step may capture its kernel sequence into CUDA graphs (OGN_GRAPHS=0 disables). dry: the step's
     // host code runs for its state transitions only, nothing is queued (the captured graph is launched instead).
     bool graphs = true, dry = false;
+    // non-null: layers append the phases they would launch to this plan (and launch nothing), see SmallPlan
+    SmallPlan *collect = nullptr;
+    bool small = true;      // OGN_SMALL_KERNEL=0 disables the single-launch path for small hierarchies
+    int smallMaxUnits = 8192;
     void forkSide();
     void learnQueued();     // call after queueing learn work on `side`
     void exchangeQueued();  // call after queueing a deferred exchange on `side`
@@ -89,9 +105,9 @@ struct DeviceContext {
     long long profileStep = 0;
     bool sampleThis = true;
     void beginStep() { sampleThis = profiling && (profileStep++ % (profilePeriod > 0 ? profilePeriod : 1)) == 0; }
-    long long timedLaunches[kKernelKinds] = {0, 0, 0, 0, 0, 0};
-    long long launches[kKernelKinds] = {0, 0, 0, 0, 0, 0};
-    double kernelMs[kKernelKinds] = {0, 0, 0, 0, 0, 0};
+    long long timedLaunches[kKernelKinds] = {0, 0, 0, 0, 0, 0, 0};
+    long long launches[kKernelKinds] = {0, 0, 0, 0, 0, 0, 0};
+    double kernelMs[kKernelKinds] = {0, 0, 0, 0, 0, 0, 0};
     struct Rec { cudaEvent_t a, b; int kind; };
     std::vector<Rec> recs;
     std::vector<cudaEvent_t> eventPool;

@@ -291,6 +291,21 @@ int ogn_checkpoint_load(const char *path, const ogn_create_options *opt, void **
         *out = H.release();
     });
 }
+int ogn_get_state(void *h, void **state_out) {
+    *state_out = nullptr;
+    return guard([&] {
+        std::unique_ptr<State> s(new State());
+        ((Handle *)h)->h.getState(*s);
+        *state_out = s.release();
+    });
+}
+int ogn_set_state(void *h, const void *state) {
+    return guard([&] {
+        if (!state) throw std::invalid_argument("ogn_set_state: null state");
+        ((Handle *)h)->h.setState(*(const State *)state);
+    });
+}
+void ogn_free_state(void *state) { delete (State *)state; }
 uint32_t ogn_rng_peek(void *h) {
     std::mt19937 c = ((Handle *)h)->cs.rng;
     return (uint32_t)c();
@@ -356,8 +371,11 @@ int64_t ogn_debug_column_weights(void *hh, int kind, int l, int vli, int ox, int
     int64_t n = -1;
     guard([&] {
         std::vector<float> w;
-        if (kind == 0) ((Handle *)hh)->h.getSCLayer(l).getColumnWeights(vli, ox, oy, w);
-        else throw std::runtime_error("ogn_debug_column_weights: kind must be 0 (SparseCoder)");
+        Hierarchy &h = ((Handle *)hh)->h;
+        if (kind == 0) h.getSCLayer(l).getColumnWeights(vli, ox, oy, w);
+        else if (kind >= 1 && kind - 1 < (int)h.getPLayers(l).size() && h.getPLayers(l)[kind - 1])
+            h.getPLayers(l)[kind - 1]->getColumnWeights(vli, ox, oy, w);
+        else throw std::runtime_error("ogn_debug_column_weights: kind must be 0 (SparseCoder) or 1 + predictor index");
         n = weightsOut(w, out, cap);
     });
     return n;

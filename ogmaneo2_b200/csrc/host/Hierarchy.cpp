@@ -30,10 +30,20 @@ struct StepGraph {
     cudaGraphExec_t exec = nullptr;
 };
 
+// The phases of one step shape, resident in device memory for the single-launch kernel (same key as the graphs).
+struct SmallStep {
+    DevBuf<ogn_small_phase> phases;
+    int nphases = 0;
+};
+
 struct Hierarchy::Impl {
     std::shared_ptr<DeviceContext> ctx;
     int batch = 1;
     std::map<std::vector<int>, StepGraph> graphs;
+    // single-launch small-hierarchy step: eligibility (-1 unknown, 0 no, 1 yes), launch shape, cached phase arrays
+    int smallOk = -1, smallBlocks = 1, smallThreads = 256, smallWide = 1;
+    std::map<std::vector<int>, SmallStep> smallSteps;
+    DevBuf<unsigned> smallCounters;
     void dropGraphs() {
         for (auto &g : graphs)
             if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
@@ -183,6 +193,49 @@ void Hierarchy::initRandomEnsemble(ComputeSystem &cs, const std::vector<unsigned
 
 int Hierarchy::getEnsembleSize() const { return impl ? impl->batch : 0; }
 
+// Whether this hierarchy steps through the single-launch kernel, and with which launch shape (decided once).
+bool Hierarchy::smallEligible(ComputeSystem &cs) {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    if (m.smallOk >= 0) return m.smallOk == 1;
+    m.smallOk = 0;
+    if (!ctx.small || ctx.useSide || cs.shardWorld != 1 || (int)inputSizes.size() > OGN_SMALL_MAX_INPUTS) return false;
+    for (auto &a : aLayers)
+        if (a) return false; // the Actor takes fresh host-drawn numbers every step
+    int units = 0, lists = 0;
+    for (size_t l = 0; l < scLayers.size(); l++) {
+        const int u = scLayers[l].smallUnits();
+        if (u < 0) return false;
+        units = std::max(units, u);
+        lists += scLayers[l].getNumVisibleLayers(); // upper bound on the layer's runs
+        for (auto &p : pLayers[l]) {
+            if (!p) continue;
+            const int pu = p->smallUnits();
+            if (pu < 0) return false;
+            units = std::max(units, pu);
+        }
+    }
+    if (units <= 0 || lists > OGN_SMALL_MAX_LISTS) return false;
+    if (m.batch > 1) { // ensemble: one block per member, one octet per pack; members never wait for each other
+        if (units > 2048) return false;
+        m.smallWide = 0; m.smallBlocks = 1;
+        m.smallThreads = std::min(512, std::max(64, ((units * 8 + 31) / 32) * 32));
+    } else {           // one hierarchy: one warp per pack over as many co-resident blocks as the largest phase can use
+        if (units > ctx.smallMaxUnits) return false;
+        m.smallWide = 1;
+        if (units <= 64) { m.smallBlocks = 1; m.smallThreads = std::min(512, 32 * units); } // one block: __syncthreads is the only barrier
+        else {
+            m.smallThreads = 256;
+            const int cap = ogn_hier_small_max_blocks(m.smallThreads);
+            if (cap < 1) return false;
+            m.smallBlocks = std::max(1, std::min((units + 7) / 8, cap));
+        }
+    }
+    m.smallCounters.allocZero((size_t)m.batch * OGN_SMALL_COUNTERS, ctx.stream);
+    m.smallOk = 1;
+    return true;
+}
+
 // Hierarchy.cpp:192-285
 void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std::vector<const int *> *devIn,
                          bool learnEnabled, float reward, bool mimic) {
@@ -194,12 +247,19 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
 
     ctx.beginStep();
     ticks[0] = 0;
+    const bool small = smallEligible(cs);
+    ogn_small_inputs smallIn;
+    std::memset(&smallIn, 0, sizeof(smallIn));
     // K1: inputs -> front of the layer-0 history rings
     if (hostIn) cudaCheck(cudaEventSynchronize(m.inFree), "cudaEventSynchronize");
     for (int i = 0; i < NI; i++) {
         Ring &r = m.histories[0][i];
         r.pushFront();
         consumeKernel1(cs, (int)(r.n / m.batch));
+        if (small && !hostIn) { // device-resident inputs: the single-launch kernel copies them itself
+            smallIn.src[i] = (*devIn)[i]; smallIn.dst[i] = r.slot(0); smallIn.count[i] = (int)(r.n / m.batch); smallIn.n = i + 1;
+            continue;
+        }
         if (hostIn) {
             // a shard only reads the input rows its slab's fields and its Predictor rows touch: copy just those
             size_t a = 0, b = r.n;
@@ -253,6 +313,7 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
             m.histories[l + 1][0].pushFront();
             copyOut = m.histories[l + 1][0].slot(0);
         }
+        if (ctx.collect) ctx.collect->curLayer = l;
         scLayers[l].stepDevice(cs, ptrs.data(), learnEnabled, copyOut);
         if (l < L - 1) {
             consumeKernel1(cs, scLayers[l].getHiddenSize().x * scLayers[l].getHiddenSize().y);
@@ -262,6 +323,7 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
     // backward (top-down) pass of the Predictors / Actors
     for (int l = L - 1; l >= 0; l--) {
         if (!updates[l]) continue;
+        if (ctx.collect) ctx.collect->curLayer = l;
         const int *fb[2] = {scLayers[l].hiddenCsDevice(), nullptr};
         if (l < L - 1) fb[1] = pLayers[l + 1][ticksPerUpdate[l + 1] - 1 - ticks[l + 1]]->hiddenCsDevice();
         for (size_t p = 0; p < pLayers[l].size(); p++) {
@@ -284,6 +346,65 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
     // stream from here on (the next step, getters, copies) is ordered behind it
     ctx.joinLearn();
     };
+
+    // Small hierarchies: the whole step is ONE launch (ogn_hier_step_small). The phases are recorded once per step shape
+    // (same key as the graphs below), ordered into barrier levels and kept in device memory; afterwards a step is the
+    // host-side state transitions plus one launch.
+    if (small) {
+        std::vector<int> key;
+        key.push_back(learnEnabled ? 1 : 0);
+        key.insert(key.end(), ticks.begin(), ticks.end());
+        for (int l = 0; l < L; l++) {
+            scLayers[l].stateSignature(key);
+            for (auto &r : m.histories[l]) key.push_back(r.start);
+            for (auto &pl : pLayers[l])
+                if (pl) pl->stateSignature(key);
+        }
+        if (m.smallSteps.size() >= 4096) m.smallSteps.clear();
+        SmallStep &ss = m.smallSteps[key];
+        if (ss.nphases == 0) {
+            SmallPlan plan;
+            ctx.collect = &plan;
+            try { body(); } catch (...) { ctx.collect = nullptr; throw; }
+            ctx.collect = nullptr;
+            if (!plan.ok) throw std::logic_error("ogmaneo-b200: single-launch plan holds a phase without a 128-bit kernel");
+            // barrier levels: with layers 0..n-1 ticking, forward(l) is level l, its reconstruction l + 1, its
+            // update l + 2 and the Predictors of layer l level n + (n - 1 - l); phases of one level are independent
+            int n = 0;
+            for (int l = 0; l < L; l++) n += updates[l] ? 1 : 0;
+            std::vector<std::pair<int, int>> order; // (level * 4 + priority inside the level, node index)
+            for (size_t i = 0; i < plan.nodes.size(); i++) {
+                const SmallPlan::Node &nd = plan.nodes[i];
+                int level = 0, prio = 0;
+                switch (nd.ph.kind) {
+                case OGN_PHASE_SC_FORWARD: level = nd.layer; prio = 0; break;
+                case OGN_PHASE_SC_RECON: level = nd.layer + 1; prio = 2; break;
+                case OGN_PHASE_SC_UPDATE: level = nd.layer + 2; prio = 3; break;
+                default: level = n + (n - 1 - nd.layer); prio = 1; break;
+                }
+                order.emplace_back(level * 4 + prio, (int)i);
+            }
+            std::stable_sort(order.begin(), order.end());
+            std::vector<ogn_small_phase> ph(order.size());
+            for (size_t i = 0; i < order.size(); i++) {
+                ph[i] = plan.nodes[order[i].second].ph;
+                ph[i].barrierAfter = (i + 1 < order.size() && order[i + 1].first / 4 != order[i].first / 4) ? 1 : 0;
+            }
+            ss.phases.alloc(ph.size());
+            cudaCheck(cudaMemcpyAsync(ss.phases.ptr(), ph.data(), ph.size() * sizeof(ogn_small_phase), cudaMemcpyHostToDevice, ctx.stream),
+                      "phase upload");
+            cudaCheck(cudaStreamSynchronize(ctx.stream), "cudaStreamSynchronize"); // `ph` is pageable and goes out of scope
+            ss.nphases = (int)ph.size();
+        } else {
+            ctx.dry = true;
+            try { body(); } catch (...) { ctx.dry = false; throw; }
+            ctx.dry = false;
+        }
+        LaunchScope ls(ctx, kHierSmall);
+        kernelCheck(ogn_hier_step_small(ss.phases.ptr(), ss.nphases, &smallIn, m.batch, m.smallBlocks, m.smallThreads, m.smallWide,
+                                        m.smallCounters.ptr(), ctx.stream), "hier_step_small");
+        return;
+    }
 
     // Graph replay (single device, single stream, no Actor: the Actor uploads fresh host-drawn numbers every step; a
     // profiled step is queued normally so that its kernels can be bracketed by events).
@@ -349,6 +470,9 @@ void Hierarchy::stepDevice(ComputeSystem &cs, const std::vector<const int *> &in
 }
 
 const int *Hierarchy::getPredictionCsDevice(int i) const {
+    // sharded: the exchange of the step's output predictions was deferred to the side stream; a caller that orders its
+    // work against the main stream (ogn_stream) must find the peers' slabs in place, so join it here
+    if (impl) impl->ctx->joinExchange();
     if (aLayers[i] != nullptr) return aLayers[i]->hiddenCsDevice();
     return pLayers.front()[i]->hiddenCsDevice();
 }

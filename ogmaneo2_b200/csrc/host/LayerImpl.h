@@ -22,6 +22,9 @@ struct SparseCoder::Impl {
     // work list of the two-kernel learn: visible columns whose reconstruction missed (8-byte entries) + {entries, warps done}
     detail::DevBuf<unsigned long long> work;
     detail::DevBuf<unsigned> workCounters;
+    // one list region per run of equally-shaped visible layers: run r owns entries [batch * runOffset[r], batch *
+    // runOffset[r + 1]) of `work`, member m of an ensemble the m-th slice of it (single-launch kernel)
+    std::vector<size_t> runOffset;
     std::vector<detail::DevBuf<int>> inStage; // standalone step(): uploaded inputs
     // host-mirror validity
     bool csDirty = true, reconDirty = true;

@@ -96,7 +96,20 @@ void Predictor::stepDevice(ComputeSystem &cs, bool learn, const int *targetDev, 
     }
     // onSideStream: a learn-only pass the caller hoisted to the side stream (see Hierarchy::step)
     cudaStream_t st = (onSideStream && ctx.useSide && !activate) ? ctx.side : ctx.stream;
-    { LaunchScope ls(ctx, kPredStep, st);
+    if (ctx.collect) { // single-launch step: record the phase instead of launching it
+        ogn_small_phase P;
+        std::memset(&P, 0, sizeof(P));
+        const int pf = Geometry::packFactor(hiddenSize.z);
+        P.kind = OGN_PHASE_PRED; P.z = hiddenSize.z; P.Hx = hiddenSize.x; P.Hy = hiddenSize.y;
+        P.ppr = (hiddenSize.y + pf - 1) / pf; P.npacks = hiddenSize.x * P.ppr;
+        P.learn = learn ? 1 : 0; P.activate = activate ? 1 : 0; P.target = targetDev; P.alpha = alpha;
+        P.acts = m.acts.ptr(); P.out0 = m.hiddenCs.ptr(); P.u.pred = a;
+        bool ok = ogn_vec_row_ok(hiddenSize.z) != 0 && m.world == 1;
+        for (int v = 0; v < nvl && ok; v++) ok = ogn_vec_geo_ok(&a.geo[a.vl[v].geo]) != 0;
+        ctx.collect->ok = ctx.collect->ok && ok;
+        ctx.collect->add(P);
+    } else {
+    LaunchScope ls(ctx, kPredStep, st);
     if (!ctx.dry) kernelCheck(ogn_pred_step(&a, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, learn ? 1 : 0, activate ? 1 : 0,
                               targetDev, alpha, m.acts.ptr(), m.hiddenCs.ptr(), st), "pred_step"); }
     if (learn) std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
@@ -202,6 +215,24 @@ void Predictor::getWeights(int i, std::vector<float> &out) const {
     w.downloadCSR(*impl->ctx, 0, out.data());
 }
 
+void Predictor::getColumnWeights(int i, int ox, int oy, std::vector<float> &out) const {
+    DeviceContext &ctx = *impl->ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    const WeightSet &w = impl->ws.sets[i];
+    const Geometry &g = *w.geo;
+    if (ox < w.fx0 || ox >= w.fx1) throw std::out_of_range("ogmaneo-b200: column not stored on this device");
+    const int64_t n = (int64_t)g.slots(ox, oy) * g.Vz * g.Hz, base = g.colBlock(ox, oy);
+    const ogn_wset d = w.desc();
+    DevBuf<float> stage;
+    stage.alloc((size_t)n);
+    const int col = oy + ox * g.Hy;
+    ctx.joinSide();
+    kernelCheck(ogn_weights_to_csr(&d, &g.host, 0, 0, col, col + 1, stage.ptr(), base, ctx.stream), "weights_to_csr");
+    out.resize((size_t)n);
+    stage.download(out.data(), (size_t)n, ctx.stream);
+    ctx.sync();
+}
+
 const Predictor::VisibleLayer &Predictor::getVisibleLayer(int i) const {
     VisibleLayer &vl = visibleLayers[i];
     if (impl->wDirty[i]) {
@@ -271,9 +302,14 @@ void Predictor::readFromStream(std::istream &is) {
 void Predictor::setState(const IntBuffer &hc, const std::vector<IntBuffer> &prev) {
     Impl &m = *impl;
     cudaCheck(cudaSetDevice(m.ctx->device), "cudaSetDevice");
-    if (hc.size() == m.hiddenCs.size()) m.hiddenCs.upload(hc.data(), hc.size(), m.ctx->stream);
-    for (size_t v = 0; v < prev.size() && v < m.prev_[m.prevCur].size(); v++)
-        if (prev[v].size() == m.prev_[m.prevCur][v].size()) m.prev_[m.prevCur][v].upload(prev[v].data(), prev[v].size(), m.ctx->stream);
+    if (hc.size() != m.hiddenCs.size()) throw std::invalid_argument("ogmaneo-b200: Predictor::setState: hiddenCs size mismatch");
+    if (prev.size() != m.prev_[m.prevCur].size()) throw std::invalid_argument("ogmaneo-b200: Predictor::setState: visible layer count mismatch");
+    for (size_t v = 0; v < prev.size(); v++)
+        if (prev[v].size() != m.prev_[m.prevCur][v].size())
+            throw std::invalid_argument("ogmaneo-b200: Predictor::setState: inputCsPrev size mismatch");
+    m.ctx->joinSide(); // a deferred exchange may still be writing hiddenCs
+    m.hiddenCs.upload(hc.data(), hc.size(), m.ctx->stream);
+    for (size_t v = 0; v < prev.size(); v++) m.prev_[m.prevCur][v].upload(prev[v].data(), prev[v].size(), m.ctx->stream);
     m.ctx->sync();
     m.csDirty = m.prevDirty = true;
 }
@@ -308,6 +344,15 @@ void Predictor::readDeviceState(std::istream &is) {
     for (WeightSet &w : m.ws.sets) readDev(is, ctx, w.wf);
     m.csDirty = m.actDirty = m.prevDirty = true;
     std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
+}
+
+int Predictor::smallUnits() const {
+    const Impl &m = *impl;
+    if (m.world > 1 || !ogn_vec_row_ok(hiddenSize.z)) return -1;
+    for (const WeightSet &w : m.ws.sets)
+        if (!ogn_vec_geo_ok(&w.geo->host)) return -1;
+    const int pf = Geometry::packFactor(hiddenSize.z);
+    return hiddenSize.x * ((hiddenSize.y + pf - 1) / pf);
 }
 
 void Predictor::stateSignature(std::vector<int> &key) const {

@@ -26,6 +26,7 @@ SparseCoder &SparseCoder::operator=(const SparseCoder &o) {
         impl->cs_[0].cloneFrom(o.impl->cs_[0], ctx.stream); impl->cs_[1].cloneFrom(o.impl->cs_[1], ctx.stream);
         impl->upd.allocZero(1, ctx.stream);
         impl->work.alloc(o.impl->work.size());
+        impl->runOffset = o.impl->runOffset;
         impl->workCounters.allocZero(2, ctx.stream);
         impl->inStage.resize(o.impl->inStage.size());
         ctx.sync();
@@ -49,13 +50,15 @@ void SparseCoder::Impl::allocate(ComputeSystem &cs, const Int3 &hidden, const st
     upd.allocZero(1, ctx->stream);
     {   // one learn launch covers a run of equally-shaped visible layers: size the list for the largest run
         size_t need = 0, v = 0;
+        runOffset.assign(1, 0);
         while (v < vlds.size()) {
             size_t e = v + 1;
             while (e < vlds.size() && ws.sets[e].geo == ws.sets[v].geo) e++;
-            need = std::max(need, (e - v) * (size_t)(ws.sets[v].vx1 - ws.sets[v].vx0) * vlds[v].size.y * batch);
+            need += (e - v) * (size_t)(ws.sets[v].vx1 - ws.sets[v].vx0) * vlds[v].size.y;
+            runOffset.push_back(need);
             v = e;
         }
-        work.alloc(std::max<size_t>(need, 1));
+        work.alloc(std::max<size_t>(need * batch, 1));
         workCounters.allocZero(2, ctx->stream);
     }
     inStage.clear(); inStage.resize(vlds.size());
@@ -102,7 +105,19 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
     const bool sharded = m.world > 1;
 
     consumeKernel2(cs, hiddenSize.x, hiddenSize.y);
-    { LaunchScope ls(ctx, kScForward);
+    if (ctx.collect) { // single-launch step: record the phase instead of launching it
+        ogn_small_phase P;
+        std::memset(&P, 0, sizeof(P));
+        P.kind = OGN_PHASE_SC_FORWARD; P.z = hiddenSize.z; P.Hx = hiddenSize.x; P.Hy = hiddenSize.y;
+        P.ppr = (hiddenSize.y + Geometry::packFactor(hiddenSize.z) - 1) / Geometry::packFactor(hiddenSize.z);
+        P.npacks = hiddenSize.x * P.ppr;
+        P.out0 = out; P.out1 = copyOut; P.u.fwd = fa;
+        bool ok = ogn_vec_row_ok(hiddenSize.z) != 0 && !sharded;
+        for (int v = 0; v < nvl && ok; v++) ok = ogn_vec_geo_ok(&fa.geo[fa.vl[v].geo]) != 0;
+        ctx.collect->ok = ctx.collect->ok && ok;
+        ctx.collect->add(P);
+    } else {
+    LaunchScope ls(ctx, kScForward);
     if (!ctx.dry) kernelCheck(ogn_sc_forward(&fa, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, out, sharded ? nullptr : copyOut,
                                ctx.stream), "sc_forward"); }
     if (sharded) {
@@ -118,8 +133,9 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
         // it overlaps whatever the caller queues next on the main stream (upper layers, the Predictors). Hierarchy::step
         // joins it at the end of the step; the host-facing step() synchronises both streams.
         cudaStream_t lst = ctx.stream;
-        if (ctx.useSide) { ctx.forkSide(); lst = ctx.side; }
-        int v = 0;
+        const bool side = ctx.useSide && !ctx.collect;
+        if (side) { ctx.forkSide(); lst = ctx.side; }
+        int v = 0, run = 0;
         while (v < nvl) { // one launch per run of visible layers with the same shape and radius
             int e = v + 1;
             while (e < nvl && m.ws.sets[e].geo == m.ws.sets[v].geo) e++;
@@ -127,13 +143,33 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
             ogn_learn_args la;
             std::memset(&la, 0, sizeof(la));
             la.geo = w0.geo->host; la.nvl = e - v; la.fx0 = w0.fx0; la.fx1 = w0.fx1;
-            la.work = m.work.ptr(); la.work_counters = m.workCounters.ptr();
+            la.work = m.work.ptr() + (size_t)m.batch * m.runOffset[run]; la.work_counters = m.workCounters.ptr();
             for (int k = v; k < e; k++) {
                 consumeKernel2(cs, visibleLayerDescs[k].size.x, visibleLayerDescs[k].size.y);
                 const WeightSet &w = m.ws.sets[k];
                 ogn_learn_vl &l = la.vl[k - v];
                 l.wf = w.fBase(); l.wr = w.rBase(); l.recon = w.recon.ptr(); l.cs = inputCsDev[k];
                 l.f_mstride = w.fCount(); l.r_mstride = w.rCount();
+            }
+            if (ctx.collect) { // single-launch step: reconstruction and update become two phases sharing one work list
+                ogn_small_phase P;
+                std::memset(&P, 0, sizeof(P));
+                const int Vz = la.geo.Vz, pr = Geometry::packFactor(Vz);
+                P.kind = OGN_PHASE_SC_RECON; P.z = Vz; P.Hx = la.geo.Vx; P.Hy = la.geo.Vy;
+                P.ppr = (la.geo.Vy + pr - 1) / pr; P.npacks = la.geo.Vx * P.ppr;
+                P.hcs = out; P.hcsPrev = prev; P.alpha = alpha; P.u.learn = la;
+                P.work = la.work; P.workStride = (int64_t)(m.runOffset[run + 1] - m.runOffset[run]);
+                P.updCount = m.upd.ptr();
+                P.counter = ctx.collect->lists++;
+                P.updVer = ogn_sc_update_version(&la); P.chunks = ogn_sc_update_chunks(&la, P.updVer);
+                const bool ok = ogn_vec_row_ok(Vz) != 0 && ogn_vec_geo_ok(&la.geo) != 0 && !sharded && P.counter < OGN_SMALL_MAX_LISTS &&
+                                P.chunks > 0;
+                ctx.collect->ok = ctx.collect->ok && ok;
+                ctx.collect->add(P);
+                P.kind = OGN_PHASE_SC_UPDATE;
+                ctx.collect->add(P);
+                v = e; run++;
+                continue;
             }
             // reconstruction (or the whole fused learn when the 128-bit path does not apply), then the work-list update
             { LaunchScope ls(ctx, kScLearn, lst);
@@ -144,9 +180,9 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
                 if (!ctx.dry) kernelCheck(ogn_sc_learn(&la, out, prev, w0.vx0, w0.vx1, alpha, m.batch, m.upd.ptr(), OGN_LEARN_UPDATE, lst),
                             "sc_update");
             }
-            v = e;
+            v = e; run++;
         }
-        if (ctx.useSide) ctx.learnQueued();
+        if (side) ctx.learnQueued();
         std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
         m.reconDirty = true;
     }
@@ -240,6 +276,7 @@ void SparseCoder::getColumnWeights(int i, int ox, int oy, std::vector<float> &ou
     DevBuf<float> stage;
     stage.alloc((size_t)n);
     const int col = oy + ox * g.Hy;
+    ctx.joinSide(); // learn may still be rewriting weights on the side stream
     kernelCheck(ogn_weights_to_csr(&d, &g.host, 0, 0, col, col + 1, stage.ptr(), base, ctx.stream), "weights_to_csr");
     out.resize((size_t)n);
     stage.download(out.data(), (size_t)n, ctx.stream);
@@ -343,6 +380,24 @@ void SparseCoder::readDeviceState(std::istream &is) {
     for (WeightSet &w : m.ws.sets) { readDev(is, ctx, w.wf); readDev(is, ctx, w.wr); readDev(is, ctx, w.recon); }
     m.csDirty = m.reconDirty = true;
     std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
+}
+
+int SparseCoder::smallUnits() const {
+    const Impl &m = *impl;
+    if (m.world > 1 || !ogn_vec_row_ok(hiddenSize.z)) return -1;
+    const int pf = Geometry::packFactor(hiddenSize.z);
+    int units = hiddenSize.x * ((hiddenSize.y + pf - 1) / pf);
+    size_t v = 0;
+    while (v < m.ws.sets.size()) {
+        size_t e = v + 1;
+        while (e < m.ws.sets.size() && m.ws.sets[e].geo == m.ws.sets[v].geo) e++;
+        const Geometry &g = *m.ws.sets[v].geo;
+        if (!ogn_vec_row_ok(g.Vz) || !ogn_vec_geo_ok(&g.host) || g.host.max_cov <= 0) return -1;
+        const int pr = Geometry::packFactor(g.Vz);
+        units = std::max(units, (int)(e - v) * g.Vx * ((g.Vy + pr - 1) / pr));
+        v = e;
+    }
+    return units;
 }
 
 void SparseCoder::stateSignature(std::vector<int> &key) const {

@@ -882,24 +882,36 @@ static inline bool vec_geo(const ogn_rf &g) {
     return (long long)g.max_nx * g.max_nyf * g.Vz < (1ll << 20) && g.max_nyf < 0xFFF && g.max_nx > 0 && g.max_nyf > 0;
 }
 // OGN_KERNELS selects the step kernels: "scalar" = the generic one-cell-per-lane kernels (always used when a row does not
-// hold 8/16/32 cells); "vec1" / "vec2" = 128-bit kernels holding 8 / 16 line loads per lane in registers; "pipe4" /
-// "pipe6" = 128-bit kernels with a cp.async ring of 4 / 6 chunks per warp in shared memory. Default (unset): vec1 for
-// launches that fill the machine (bandwidth-bound: the extra registers of vec2 only cost occupancy) and vec2 for small
-// launches (latency-bound: twice the loads in flight per lane shorten the dependent chain; C2 +19 %), see
-// profiles/README.md.
-constexpr int kAutoVariant = 9;
+// hold 8/16/32 cells); "vec1" / "vec2" = 128-bit kernels, one octet per pack, 8 / 16 line loads per lane in registers;
+// "tma" = vec1 with the input CSDR windows of a block staged in shared memory by the bulk-copy (TMA) engine; "wide" /
+// "wide2" = one warp per pack (four octets share a pack's chunks; 8 / 16 loads per lane). Default (unset): large launches
+// (bandwidth-bound) take vec1, small launches (latency-bound, at most kSmallLaunchPacks packs x members) take the
+// variant OGN_SMALL_VARIANT names (default below), see profiles/README.md.
+constexpr int kVarScalar = 0, kVarVec1 = 1, kVarVec2 = 2, kVarTma = 7, kVarWide = 8, kVarWide2 = 10, kAutoVariant = 9;
 constexpr long long kSmallLaunchPacks = 8192; // packs x members at or below which a launch counts as latency-bound
+static int parse_variant(const char *e, int dflt) {
+    if (!e) return dflt;
+    if (!strcmp(e, "scalar")) return kVarScalar;
+    if (!strcmp(e, "vec1")) return kVarVec1;
+    if (!strcmp(e, "vec2")) return kVarVec2;
+    if (!strcmp(e, "tma")) return kVarTma;
+    if (!strcmp(e, "wide")) return kVarWide;
+    if (!strcmp(e, "wide2")) return kVarWide2;
+    return dflt;
+}
 static int kernel_variant() {
     static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("OGN_KERNELS");
-        v = kAutoVariant;
-        if (e && !strcmp(e, "scalar")) v = 0;
-        else if (e && !strcmp(e, "vec1")) v = 1;
-        else if (e && !strcmp(e, "vec2")) v = 2;
-        else if (e && !strcmp(e, "pipe4")) v = 4;
-        else if (e && !strcmp(e, "pipe6")) v = 6;
-    }
+    if (v < 0) v = parse_variant(getenv("OGN_KERNELS"), kAutoVariant);
+    return v;
+}
+static int small_variant() {
+    static int v = -1;
+    if (v < 0) v = parse_variant(getenv("OGN_SMALL_VARIANT"), kVarWide);
+    return v;
+}
+static int large_variant() {
+    static int v = -1;
+    if (v < 0) v = parse_variant(getenv("OGN_LARGE_VARIANT"), kVarVec1);
     return v;
 }
 
@@ -909,18 +921,25 @@ static int env_int(const char *name, int dflt) {
 }
 static int resolve_variant(long long packs) { // the variant one launch over `packs` packs (x members) uses
     const int v = kernel_variant();
-    return v == kAutoVariant ? (packs <= kSmallLaunchPacks ? 2 : 1) : v;
+    static long long small = -1;
+    if (small < 0) small = env_int("OGN_SMALL_PACKS", (int)kSmallLaunchPacks);
+    return v == kAutoVariant ? (packs <= small ? small_variant() : large_variant()) : v;
 }
-static bool is_pipe(int variant) { return variant == 4 || variant == 6; }
+static bool is_wide(int variant) { return variant == kVarWide || variant == kVarWide2; }
 static int vec_threads(int variant) { // threads per block of the 128-bit kernels (a multiple of 32, at most 256); OGN_VEC_THREADS overrides
     static int env = -1;
     if (env < 0) env = env_int("OGN_VEC_THREADS", 0);
-    int v = env ? env : (is_pipe(variant) ? 128 : kThreads);
+    int v = env ? env : kThreads;
     if (v < 32 || v > kThreads || v % 32) v = kThreads;
     return v;
 }
-static size_t ring_bytes(int variant, int threads) { // cp.async ring: D stages x 8 lines x 32 lanes x 16 bytes per warp
-    return (size_t)(threads / 32) * (is_pipe(variant) ? variant : 0) * 4096;
+// launches per (kernel: 0 sc_forward, 1 sc_recon, 2 pred_step; variant column: 0 scalar, 1 vec1, 2 vec2, 3 / 4 unused (the
+// cp.async ring variants of round 1), 5 tma, 6 wide, 7 wide2) since the library was loaded: lets a test assert which kernel
+// a size actually ran (ogn_debug_variant_launches)
+static long long g_variantLaunches[3][8];
+static void count_variant(int kernel, int variant) {
+    const int col = variant == kVarScalar ? 0 : variant == kVarVec1 ? 1 : variant == kVarVec2 ? 2 : variant == kVarTma ? 5 : variant == kVarWide ? 6 : 7;
+    g_variantLaunches[kernel][col]++;
 }
 
 } // extern "C"
@@ -936,6 +955,7 @@ static void launch_k(void (*k)(P...), dim3 grid, int threads, size_t smem, cudaS
     }
     k<<<grid, threads, smem, st>>>(a...);
 }
+
 extern "C" {
 
 #define OGN_DISPATCH_Z(Z_, CALL)                     \
@@ -944,14 +964,46 @@ extern "C" {
     case 16: { constexpr int Z = 16; CALL; } break;  \
     default: { constexpr int Z = 32; CALL; } break;  \
     }
-// CALL sees the compile-time constants Z, NCH (register batch depth) and D (cp.async ring depth, 0 = registers)
+// CALL sees the compile-time constants Z, NCH (register batch depth) and W (lanes per pack)
 #define OGN_DISPATCH_VEC(VARIANT_, Z_, CALL)                                                    \
     switch (VARIANT_) {                                                                         \
-    case 2: { constexpr int NCH = 2, D = 0; OGN_DISPATCH_Z(Z_, CALL); } break;                  \
-    case 4: { constexpr int NCH = 1, D = 4; OGN_DISPATCH_Z(Z_, CALL); } break;                  \
-    case 6: { constexpr int NCH = 1, D = 6; OGN_DISPATCH_Z(Z_, CALL); } break;                  \
-    default: { constexpr int NCH = 1, D = 0; OGN_DISPATCH_Z(Z_, CALL); } break;                 \
+    case kVarVec2: { constexpr int NCH = 2, W = 8; OGN_DISPATCH_Z(Z_, CALL); } break;           \
+    case kVarWide: { constexpr int NCH = 1, W = 32; OGN_DISPATCH_Z(Z_, CALL); } break;          \
+    case kVarWide2: { constexpr int NCH = 2, W = 32; OGN_DISPATCH_Z(Z_, CALL); } break;         \
+    default: { constexpr int NCH = 1, W = 8; OGN_DISPATCH_Z(Z_, CALL); } break;                 \
     }
+
+// ints per staged CSDR window for a launch whose blocks hold `ppb` packs of one row, or 0 if the geometry cannot be staged:
+// window width <= (y extent the ppb packs' union fields span) rounded out to multiples of 4, height <= max_nx. The bound
+// uses only scalars of ogn_rf (max_nyf, pf and the grid ratio), so no table has to be read back from the device.
+static int tile_ints(const ogn_rf &g, int ppb) {
+    if (g.Vy % 4 != 0 || g.max_nx <= 0 || g.max_nyf <= 0) return 0;
+    if (!g.tma_ok) return 0; // host-side geometry check: non-empty, monotone union fields
+    // union field of pack q starts at project(q * pf) - r (clamped): consecutive packs advance by at most
+    // ceil(pf * Vy / Hy) + 1 visible columns, so ppb packs span at most that times (ppb - 1) plus the widest field
+    const long long adv = ((long long)g.pf * g.Vy + g.Hy - 1) / g.Hy + 1;
+    long long w = adv * (ppb - 1) + g.max_nyf + 6; // + 6: both ends rounded out to multiples of 4
+    w = (w + 3) & ~3ll;
+    if (w > g.Vy) w = g.Vy; // Vy % 4 == 0
+    const long long ints = w * g.max_nx;
+    return ints > 0 && ints < (1 << 14) ? (int)ints : 0;
+}
+
+int ogn_vec_row_ok(int z) { return vec_row(z) ? 1 : 0; }
+int ogn_vec_geo_ok(const ogn_rf *g) { return vec_geo(*g) ? 1 : 0; }
+int ogn_sc_update_version(const ogn_learn_args *args) {
+    static int forced = -1;
+    if (forced < 0) forced = env_int("OGN_SC_UPDATE", 0);
+    const bool v2ok = args->geo.Hz % 8 == 0;
+    if (forced == 1) return 1;
+    if (forced == 2) return v2ok ? 2 : 1;
+    return v2ok ? 2 : 1;
+}
+int ogn_sc_update_chunks(const ogn_learn_args *args, int version) {
+    const int Vz = args->geo.Vz;
+    const int items = version == 2 ? ((2 * Vz >= 32 ? 1 : 32 / (2 * Vz)) * 4) : (32 / (Vz / 4)) * 4;
+    return (args->geo.max_cov + items - 1) / items;
+}
 
 int ogn_sc_forward(const ogn_fwd_args *args, int Hx, int Hy, int Hz, int x0, int x1, int batch, int *hidden_cs, int *hidden_cs2,
                    void *stream) {
@@ -965,12 +1017,34 @@ int ogn_sc_forward(const ogn_fwd_args *args, int Hx, int Hy, int Hz, int x0, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (vecOk) {
-        const int var = resolve_variant((long long)npacks * batch), vt = vec_threads(var);
-        dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
-        OGN_DISPATCH_VEC(var, Hz, (launch_k(vec::k_sc_forward_v<Z, NCH, D>, grid, vt, ring_bytes(var, vt), st, *args, Hx, Hy, x0, npacks,
-                                            ppr, hidden_cs, hidden_cs2)));
+        int var = resolve_variant((long long)npacks * batch);
+        const int vt = vec_threads(var);
+        if (var == kVarTma) { // staged CSDR windows: every visible layer must be eligible, else plain vec1
+            int ti = 0;
+            bool ok = ppr % (vt / 8) == 0 && args->nvl <= 8;
+            for (int v = 0; v < args->nvl && ok; v++) {
+                const int t = tile_ints(args->geo[args->vl[v].geo], vt / 8);
+                ok = t > 0;
+                ti = t > ti ? t : ti;
+            }
+            const size_t smem = (size_t)args->nvl * ti * sizeof(int) + 16;
+            if (ok && smem <= 96u * 1024u) {
+                count_variant(0, kVarTma);
+                dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
+                OGN_DISPATCH_Z(Hz, (launch_k(vec::k_sc_forward_t<Z, 1>, grid, vt, smem, st, *args, Hx, Hy, x0, npacks, ppr, ti, hidden_cs,
+                                             hidden_cs2)));
+                return launch_status();
+            }
+            var = kVarVec1;
+        }
+        count_variant(0, var);
+        const int lanes = is_wide(var) ? 32 : 8;
+        dim3 grid((unsigned)(((long long)npacks * lanes + vt - 1) / vt), (unsigned)batch);
+        OGN_DISPATCH_VEC(var, Hz, (launch_k(vec::k_sc_forward_v<Z, NCH, W>, grid, vt, 0, st, *args, Hx, Hy, x0, npacks, ppr, hidden_cs,
+                                            hidden_cs2)));
         return launch_status();
     }
+    count_variant(0, 0);
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);
     OGN_DISPATCH_G(g, (k_sc_forward<G><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, Hz, x0, npacks, ppr, hidden_cs, hidden_cs2)));
     return launch_status();
@@ -989,29 +1063,38 @@ int ogn_sc_learn(const ogn_learn_args *args, const int *hidden_cs, const int *hi
     cudaStream_t st = (cudaStream_t)stream;
     if (ogn_sc_learn_is_split(args)) {
         const int Vz = args->geo.Vz;
-        const int var = resolve_variant((long long)npacks * batch * args->nvl), vt = vec_threads(var);
-        dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch, (unsigned)args->nvl);
+        int var = resolve_variant((long long)npacks * batch * args->nvl);
+        if (var == kVarTma) var = kVarVec1; // the reconstruction has no staged variant
+        const int vt = vec_threads(var);
+        const int lanes = is_wide(var) ? 32 : 8;
+        dim3 grid((unsigned)(((long long)npacks * lanes + vt - 1) / vt), (unsigned)batch, (unsigned)args->nvl);
         int2 *work = (int2 *)args->work;
         unsigned *cnt = args->work_counters;
         if (phase != OGN_LEARN_UPDATE) {
-            OGN_DISPATCH_VEC(var, Vz, (launch_k(vec::k_sc_recon_v<Z, NCH, D>, grid, vt, ring_bytes(var, vt), st, *args, hidden_cs, vx0,
-                                                npacks, ppr, work, cnt)));
+            count_variant(1, var);
+            OGN_DISPATCH_VEC(var, Vz, (launch_k(vec::k_sc_recon_v<Z, NCH, W>, grid, vt, 0, st, *args, hidden_cs, vx0, npacks, ppr, work, cnt)));
             int e = launch_status();
             if (e || phase == OGN_LEARN_RECONSTRUCT) return e;
         }
-        // persistent grid over the work units (chunks of 32/LC * 4 cover items of a listed column): enough warps to fill the
-        // machine, never more than one per possible unit
-        const int itemsPerUnit = (32 / (Vz / 4)) * 4;
-        const int chunks = (args->geo.max_cov + itemsPerUnit - 1) / itemsPerUnit;
+        // persistent grid over the work units (chunks of cover items of a listed column): enough warps to fill the machine,
+        // never more than one per possible unit
+        const int ver = ogn_sc_update_version(args);
+        const int chunks = ogn_sc_update_chunks(args, ver);
         if (chunks <= 0) return 0;
         long long maxUnits = (long long)(vx1 - vx0) * args->geo.Vy * batch * args->nvl * chunks;
         long long blocks = (maxUnits + (kThreads / 32) - 1) / (kThreads / 32);
         if (blocks > update_grid_blocks()) blocks = update_grid_blocks();
-        OGN_DISPATCH_Z(Vz, (vec::k_sc_update_v<Z><<<(unsigned)blocks, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, work, cnt, cnt + 1,
-                                                                                      alpha, update_count, chunks)));
+        if (ver == 2) {
+            OGN_DISPATCH_Z(Vz, (vec::k_sc_update_v<Z, 2><<<(unsigned)blocks, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, work, cnt,
+                                                                                             cnt + 1, alpha, update_count, chunks)));
+        } else {
+            OGN_DISPATCH_Z(Vz, (vec::k_sc_update_v<Z, 1><<<(unsigned)blocks, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, work, cnt,
+                                                                                             cnt + 1, alpha, update_count, chunks)));
+        }
         return launch_status();
     }
     if (phase == OGN_LEARN_UPDATE) return 0;
+    count_variant(1, 0);
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch, (unsigned)args->nvl);
     OGN_DISPATCH_G(g, (k_sc_learn<G><<<grid, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, vx0, npacks, ppr, alpha, update_count)));
     return launch_status();
@@ -1029,16 +1112,65 @@ int ogn_pred_step(const ogn_pred_args *args, int Hx, int Hy, int Hz, int x0, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (vecOk) {
-        const int var = resolve_variant((long long)npacks * batch), vt = vec_threads(var);
-        dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
-        OGN_DISPATCH_VEC(var, Hz, (launch_k(vec::k_pred_step_v<Z, NCH, 1, D>, grid, vt, ring_bytes(var, vt), st, *args, Hx, Hy, x0,
-                                            npacks, ppr, learn, activate, target_cs, alpha, activations, hidden_cs)));
+        int var = resolve_variant((long long)npacks * batch);
+        const int vt = vec_threads(var);
+        if (var == kVarTma) {
+            int ti = 0;
+            bool ok = ppr % (vt / 8) == 0 && args->nvl <= 4;
+            for (int v = 0; v < args->nvl && ok; v++) {
+                const int t = tile_ints(args->geo[args->vl[v].geo], vt / 8);
+                ok = t > 0;
+                ti = t > ti ? t : ti;
+            }
+            const size_t smem = (size_t)2 * args->nvl * ti * sizeof(int) + 16;
+            if (ok && smem <= 96u * 1024u) {
+                count_variant(2, kVarTma);
+                dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
+                OGN_DISPATCH_Z(Hz, (launch_k(vec::k_pred_step_t<Z, 1, 1>, grid, vt, smem, st, *args, Hx, Hy, x0, npacks, ppr, ti, learn,
+                                             activate, target_cs, alpha, activations, hidden_cs)));
+                return launch_status();
+            }
+            var = kVarVec1;
+        }
+        count_variant(2, var);
+        const int lanes = is_wide(var) ? 32 : 8;
+        dim3 grid((unsigned)(((long long)npacks * lanes + vt - 1) / vt), (unsigned)batch);
+        OGN_DISPATCH_VEC(var, Hz, (launch_k(vec::k_pred_step_v<Z, NCH, 1, W>, grid, vt, 0, st, *args, Hx, Hy, x0, npacks, ppr, learn,
+                                            activate, target_cs, alpha, activations, hidden_cs)));
         return launch_status();
     }
+    count_variant(2, 0);
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads), (unsigned)batch);
     OGN_DISPATCH_G(g, (k_pred_step<G><<<grid, kThreads, 0, st>>>(*args, Hx, Hy, Hz, x0, npacks, ppr, learn, activate, target_cs, alpha,
                                                               activations, hidden_cs)));
     return launch_status();
+}
+
+int ogn_hier_small_max_blocks(int threads) {
+    int dev = 0, sms = 0, per = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, vec::k_hier_step_small<32>, threads, 0) != cudaSuccess) return 0;
+    return sms * per;
+}
+
+int ogn_hier_step_small(const ogn_small_phase *phases, int nphases, const ogn_small_inputs *inputs, int members, int blocks_per_member,
+                        int threads, int wide, unsigned *counters, void *stream) {
+    if (nphases <= 0 || members <= 0) return 0;
+    if (blocks_per_member < 1 || threads < 32 || threads > 512 || threads % 32) return (int)cudaErrorInvalidValue;
+    dim3 grid((unsigned)blocks_per_member, (unsigned)members);
+    int cpm = OGN_SMALL_COUNTERS;
+    ogn_small_inputs in;
+    memset(&in, 0, sizeof(in));
+    if (inputs) in = *inputs;
+    if (blocks_per_member == 1) {
+        if (wide) vec::k_hier_step_small<32><<<grid, threads, 0, (cudaStream_t)stream>>>(phases, nphases, in, counters, cpm);
+        else vec::k_hier_step_small<8><<<grid, threads, 0, (cudaStream_t)stream>>>(phases, nphases, in, counters, cpm);
+        return launch_status();
+    }
+    void *kargs[] = {(void *)&phases, (void *)&nphases, (void *)&in, (void *)&counters, (void *)&cpm};
+    const void *fn = wide ? (const void *)vec::k_hier_step_small<32> : (const void *)vec::k_hier_step_small<8>;
+    return (int)cudaLaunchCooperativeKernel(fn, grid, dim3((unsigned)threads), kargs, 0, (cudaStream_t)stream);
 }
 
 int ogn_actor_forward(const ogn_actor_args *args, int Hx, int Hy, int Hz, const float *u01, float *hidden_values,
@@ -1118,6 +1250,8 @@ int ogn_weights_fr_mismatch(const ogn_wset *ws, const ogn_rf *rf, int member, un
                                                                         xa * rf->Hy, count_dev);
     return launch_status();
 }
+
+void ogn_debug_variant_launches(long long out[24]) { memcpy(out, g_variantLaunches, sizeof(g_variantLaunches)); }
 
 int ogn_test_expf(const float *in, float *out, int64_t n, void *stream) {
     if (n <= 0) return 0;

@@ -83,6 +83,9 @@ _SIGS = {
     "set_actor_params": (C.c_int, [_VP, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]),
     "save": (C.c_int64, [_VP, C.c_char_p]),
     "load": (C.c_int, [C.c_char_p, C.c_uint32, C.POINTER(_VP)]),
+    "get_state": (C.c_int, [_VP, C.POINTER(_VP)]),
+    "set_state": (C.c_int, [_VP, _VP]),
+    "free_state": (None, [_VP]),
     "rng_peek": (C.c_uint32, [_VP]),
 }
 
@@ -110,6 +113,21 @@ def _ip(a: np.ndarray):
 
 def _fp(a: np.ndarray):
     return a.ctypes.data_as(_FP)
+
+
+class HierarchyState:
+    """Opaque ogmaneo::State (Hierarchy.h:26-36) owned by Python; freed with the object."""
+
+    def __init__(self, flat: FlatLib, s):
+        self.f, self.s = flat, s
+
+    def __del__(self):
+        try:
+            if self.s:
+                self.f.free_state(self.s)
+                self.s = None
+        except Exception:
+            pass
 
 
 class FlatHierarchy:
@@ -230,6 +248,16 @@ class FlatHierarchy:
         return n
 
     def rngPeek(self) -> int: return int(self.f.rng_peek(self.h))
+
+    def getState(self) -> "HierarchyState":
+        """Hierarchy::getState (Hierarchy.cpp:434-466): a snapshot of every CSDR, history ring, tick and update flag."""
+        s = _VP()
+        self._chk(self.f.get_state(self.h, C.byref(s)), "get_state")
+        return HierarchyState(self.f, s)
+
+    def setState(self, state: "HierarchyState"):
+        """Hierarchy::setState (Hierarchy.cpp:468-493): rewind to a snapshot taken from this (or an identical) hierarchy."""
+        self._chk(self.f.set_state(self.h, state.s), "set_state")
 
     # --- everything the parity tests compare, as one dict ------------------------------------------------------
     def snapshot(self, weights: bool = False) -> dict:

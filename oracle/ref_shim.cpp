@@ -161,6 +161,18 @@ int oref_load(const char *path, uint32_t seed, void **out) {
     *out = H;
     return 0;
 }
+int oref_get_state(void *h, void **state_out) {
+    auto *s = new State();
+    ((Handle *)h)->h.getState(*s);
+    *state_out = s;
+    return 0;
+}
+int oref_set_state(void *h, const void *state) {
+    if (!state) return fail("null state");
+    ((Handle *)h)->h.setState(*(const State *)state);
+    return 0;
+}
+void oref_free_state(void *state) { delete (State *)state; }
 uint32_t oref_rng_peek(void *h) {
     std::mt19937 c = ((Handle *)h)->cs.rng;
     return (uint32_t)c();

@@ -779,5 +779,48 @@ int oport_load(const char *path, uint32_t seed, void **out) {
     *out = h;
     return 0;
 }
+// Hierarchy::getState / setState, Hierarchy.cpp:434-493: every CSDR, the history rings, ticks and updates (no weights)
+struct PortState {
+    std::vector<IntBuf> hiddenCs, hiddenCsPrev;
+    std::vector<std::vector<IntBuf>> predHiddenCs;
+    std::vector<std::vector<std::vector<IntBuf>>> predInputCsPrev;
+    std::vector<std::vector<History>> histories;
+    std::vector<char> updates;
+    std::vector<int> ticks;
+};
+int oport_get_state(void *hh, void **state_out) {
+    const Hierarchy &h = *(Hierarchy *)hh;
+    auto *s = new PortState();
+    const size_t L = h.sc.size();
+    s->hiddenCs.resize(L); s->hiddenCsPrev.resize(L); s->predHiddenCs.resize(L); s->predInputCsPrev.resize(L);
+    for (size_t l = 0; l < L; l++) {
+        s->hiddenCs[l] = h.sc[l].hiddenCs; s->hiddenCsPrev[l] = h.sc[l].hiddenCsPrev;
+        s->predHiddenCs[l].resize(h.p[l].size()); s->predInputCsPrev[l].resize(h.p[l].size());
+        for (size_t j = 0; j < h.p[l].size(); j++) {
+            if (!h.p[l][j]) continue;
+            s->predHiddenCs[l][j] = h.p[l][j]->hiddenCs;
+            for (auto &vl : h.p[l][j]->vls) s->predInputCsPrev[l][j].push_back(vl.inputCsPrev);
+        }
+    }
+    s->histories = h.histories; s->updates = h.updates; s->ticks = h.ticks;
+    *state_out = s;
+    return 0;
+}
+int oport_set_state(void *hh, const void *state) {
+    if (!state) { g_err = "null state"; return 1; }
+    Hierarchy &h = *(Hierarchy *)hh;
+    const PortState &s = *(const PortState *)state;
+    for (size_t l = 0; l < h.sc.size(); l++) {
+        h.sc[l].hiddenCs = s.hiddenCs[l]; h.sc[l].hiddenCsPrev = s.hiddenCsPrev[l];
+        for (size_t j = 0; j < h.p[l].size(); j++) {
+            if (!h.p[l][j]) continue;
+            h.p[l][j]->hiddenCs = s.predHiddenCs[l][j];
+            for (size_t v = 0; v < h.p[l][j]->vls.size(); v++) h.p[l][j]->vls[v].inputCsPrev = s.predInputCsPrev[l][j][v];
+        }
+    }
+    h.histories = s.histories; h.updates = s.updates; h.ticks = s.ticks;
+    return 0;
+}
+void oport_free_state(void *state) { delete (PortState *)state; }
 uint32_t oport_rng_peek(void *h) { std::mt19937 c = ((Hierarchy *)h)->cs.rng; return (uint32_t)c(); }
 } // extern "C"

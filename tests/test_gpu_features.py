@@ -215,8 +215,16 @@ def test_peer_memory_exchange_multi_gpu(product):
     assert r.stdout.count(" ok") == world
 
 
-def test_get_set_state_and_copy_semantics(product):
-    """Hierarchy::getState/setState round trip through the flat ABI's save/load + continued stepping determinism."""
+def test_get_set_state_rewinds_like_the_reference(product, oracle):
+    """Hierarchy::getState / setState through ogn_get_state / ogn_set_state against the checker's (Hierarchy.cpp:434-493):
+    rewind + replay reproduces the first pass, and learning after a rewind stays bit-identical to the checker."""
+    from test_oracle import state_rewind_check
+    flat, kind = oracle
+    flat.set_num_threads(1)
+    state_rewind_check(maker(product.lib()), maker(flat), configs.c2_video(8, 3), f"device vs {kind}")
+
+
+def test_two_identical_runs_are_deterministic(product):
     cfg = configs.c2_video(8, 3)
     a = product.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=21)
     b = product.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=21)

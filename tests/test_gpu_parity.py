@@ -40,6 +40,61 @@ def test_c5_unit(product, oracle):
     _check(product, oracle, configs.c5_unit(16), 40, check_every=5)
 
 
+def _variant_counts(product):
+    """launches per (kernel kind, variant) since the library was loaded: rows sc_forward, sc_recon, pred_step;
+    columns scalar, vec1, vec2, pipe4, pipe6, tma"""
+    import ctypes as C
+    out = (C.c_longlong * 24)()
+    product.cdll().ogn_debug_variant_launches(out)
+    return np.array(list(out), dtype=np.int64).reshape(3, 8)
+
+
+def _check_contract_size(product, oracle, cfg, steps, want_vec1):
+    """BASELINE-size parity with the DEFAULT kernel selector: every CSDR, activation and weight against the
+    compiled reference running on all host threads (no Actor, so the reference is thread-count independent; its shared
+    RNG is not, so the RNG state is not compared here)."""
+    import os
+    flat, kind = oracle
+    assert "OGN_KERNELS" not in os.environ, "this test pins the default selector"
+    flat.set_num_threads(os.cpu_count() or 1)
+    before = _variant_counts(product)
+    err = run_pair(cfg, steps, maker(product.lib()), maker(flat), check_every=3, compare_rng=False)
+    flat.set_num_threads(1)
+    assert err is None, f"[checker={kind}] {err}"
+    used = _variant_counts(product) - before
+    for row, name in want_vec1:
+        assert used[row, 1] > 0, f"{name} never ran as vec1 (the headline kernel) at this size: {used[row].tolist()}"
+
+
+def test_c2_video_full_size(product, oracle):
+    """BASELINE config 2 at its stated size: 32x32x16 input, 3 layers of 32x32x32, radius 3."""
+    _check_contract_size(product, oracle, configs.c2_video(32, 3), 24, want_vec1=[])
+
+
+def test_c4_large_layer_at_oracle_size_128(product, oracle):
+    """BASELINE config 4 at SURVEY's oracle size 128x128 (1.3e9 weights): the SparseCoder forward runs the headline vec1
+    kernel under the default selector."""
+    _check_contract_size(product, oracle, configs.c4_large(128), 10, want_vec1=[(0, "sc_forward")])
+
+
+def test_c4_large_layer_160_all_headline_kernels(product, oracle):
+    """160x160 (2.1e9 weights, the reference needs ~25 GB): the smallest square size at which the default selector picks
+    vec1 for ALL of forward, reconstruction and Predictor (more than 8192 packs per launch), i.e. exactly the kernels
+    bench.py times at 512x512."""
+    _check_contract_size(product, oracle, configs.c4_large(160), 8,
+                         want_vec1=[(0, "sc_forward"), (1, "sc_recon"), (2, "pred_step")])
+
+
+def test_c4_large_layer_224_opt_in(product, oracle):
+    """The largest size the reference can construct (224x224, 4.1e9 weights, ~45 GiB of host memory, two
+    minutes of reference init). Opt-in: OGN_TEST_C4_224=1."""
+    import os
+    if os.environ.get("OGN_TEST_C4_224") != "1":
+        pytest.skip("opt-in (OGN_TEST_C4_224=1): needs ~60 GB of host memory and ~4 minutes")
+    _check_contract_size(product, oracle, configs.c4_large(224), 6,
+                         want_vec1=[(0, "sc_forward"), (1, "sc_recon"), (2, "pred_step")])
+
+
 @pytest.mark.parametrize("shape", [
     dict(inp=(5, 7, 6), hid=(3, 4, 5), r=1),      # downsampling, non-square, Z not a power of two
     dict(inp=(2, 3, 4), hid=(6, 5, 8), r=2),      # upsampling: fields overlap and clamp everywhere
@@ -94,18 +149,21 @@ def test_actor_more_history_samples_than_one_launch_holds(product, oracle):
 
 
 @pytest.mark.parametrize("env", [
-    {"OGN_KERNELS": "scalar"}, {"OGN_KERNELS": "vec1"}, {"OGN_KERNELS": "vec2"}, {"OGN_KERNELS": "pipe4"}, {"OGN_KERNELS": "pipe6"},
-    {"OGN_GRAPHS": "0"}, {"OGN_SIDE_STREAM": "1"},
+    {"OGN_KERNELS": "scalar"}, {"OGN_KERNELS": "vec1"}, {"OGN_KERNELS": "vec2"}, {"OGN_KERNELS": "tma"}, {"OGN_KERNELS": "wide"},
+    {"OGN_KERNELS": "wide2"}, {"OGN_KERNELS": "vec1", "OGN_SC_UPDATE": "1"}, {"OGN_SMALL_KERNEL": "0"},
+    {"OGN_SMALL_KERNEL": "0", "OGN_GRAPHS": "0"}, {"OGN_SMALL_KERNEL": "0", "OGN_SIDE_STREAM": "1"},
 ], ids=lambda e: "-".join(f"{k[4:].lower()}={v}" for k, v in e.items()))
 def test_every_kernel_variant_and_scheduling_mode_is_bit_exact(env):
-    """The alternative kernels (generic one-cell-per-lane, deeper register batches, cp.async rings) and scheduling modes
-    (no CUDA graphs, side stream on one GPU) are selected per process: rerun a parity subset in a subprocess for each."""
+    """The alternative kernels (generic one-cell-per-lane, deeper register batches, TMA-staged CSDR windows, one warp per
+    pack, the partial-sector update kernel) and scheduling modes (per-phase launches instead of the single-launch step,
+    with and without CUDA graphs, side stream on one GPU) are selected per process: rerun a parity subset in a subprocess
+    for each. The default run of this file covers the single-launch kernel, `wide` for small launches and update v2."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
-           "-k", "c2_video_small or c4_large_layer_small or c1_sine or odd"]
+           "-k", "c2_video_small or c4_large_layer_small or c1_sine or odd or c5_unit"]
     r = subprocess.run(cmd, cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
@@ -143,13 +201,7 @@ def test_random_shapes_inner(product, oracle, seed):
     _check(product, oracle, random_cfg(seed), 24, check_every=4)
 
 
-# Written when this round's GPU budget was all but spent. The last 4 seconds of it ran seeds 0 and 1: seed 0 passed, seed 1
-# differed only in the BITS of NaN activations (a Predictor column whose radius-0 field is empty divides 0 by 0: x86 gives
-# the default NaN 0xFFC00000, the GPU 0x7FFFFFFF); div_ref() in ogn_kernels.cu now maps those to the x86 value, but that
-# fix and seeds 2-15 have not run on a B200. Hence: a subprocess (a device fault cannot poison the CUDA context of the
-# tests that follow) and a non-strict xfail (an unverified test cannot turn the suite red: a pass shows as XPASS, a
-# mismatch as XFAIL with the subprocess report). Drop the marker after the first full GPU run.
-@pytest.mark.xfail(strict=False, reason="seeds 2-15 and the NaN-bits fix have not run on a B200 yet (GPU budget spent)")
+# A subprocess, so that a device fault on one odd shape cannot poison the CUDA context of the tests that follow.
 def test_random_shapes():
     import os
     import subprocess

@@ -159,3 +159,49 @@ def test_port_vs_reference_on_random_shapes(seed):
     port.set_num_threads(0)
     err = run_pair(random_cfg(seed), 24, maker(port), maker(ref), check_every=4, compare_rng=True)
     assert err is None, err
+
+
+def state_rewind_check(mk_a, mk_b, cfg, label):
+    """Hierarchy::getState / setState (Hierarchy.cpp:434-493) through the flat ABI on two implementations side by side:
+    snapshot after some learning, run on without learning, rewind both, replay: the replay must reproduce the first pass,
+    and learning steps after the rewind must keep both implementations bit-identical (weights included)."""
+    a, b = mk_a(cfg), mk_b(cfg)
+    for t in range(17):
+        ins = make_inputs(cfg, t)
+        a.step(ins, True)
+        b.step(ins, True)
+    sa, sb = a.getState(), b.getState()
+    first = []
+    for t in range(17, 30):
+        ins = make_inputs(cfg, t)
+        a.step(ins, False)
+        b.step(ins, False)
+        first.append((a.getPredictionCs(0), [a.scHiddenCs(l) for l in range(a.getNumLayers())]))
+        assert np.array_equal(first[-1][0], b.getPredictionCs(0)), f"{label}: prediction differs at step {t}"
+    a.setState(sa)
+    b.setState(sb)
+    d = diff_snapshots(a.snapshot(False), b.snapshot(False))
+    assert not d, f"{label}: state differs right after setState: {d[:3]}"
+    for k, t in enumerate(range(17, 30)):
+        ins = make_inputs(cfg, t)
+        a.step(ins, False)
+        b.step(ins, False)
+        assert np.array_equal(a.getPredictionCs(0), first[k][0]), f"{label}: replay after setState differs at step {t}"
+        for l in range(a.getNumLayers()):
+            assert np.array_equal(a.scHiddenCs(l), first[k][1][l]), f"{label}: replayed hidden CSDR {l} differs at step {t}"
+    a.setState(sa)
+    b.setState(sb)
+    for t in range(30, 42):  # learning after a rewind: both sides learn from the same (stale) activations
+        ins = make_inputs(cfg, t)
+        a.step(ins, True)
+        b.step(ins, True)
+    d = diff_snapshots(a.snapshot(True), b.snapshot(True))
+    assert not d, f"{label}: {d[:3]}"
+
+
+def test_port_get_set_state_like_the_reference():
+    ref = loader.ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no reference sources on this box)")
+    ref.set_num_threads(1)
+    state_rewind_check(maker(loader.port()), maker(ref), configs.c2_video(8, 3), "port vs reference")
