@@ -502,11 +502,33 @@ def main():
     Ke = K
     barrier()
     pred_idx = [i for i, t in enumerate(cfg["inputTypes"]) if t != InputType.none]
+    # streaming callers collect the prediction of step t after queueing step t + 1 (ogn_prediction_readback_queue/finish:
+    # one step of pipelining, pinned slots on a copy stream); a shard reads back ITS slab of the prediction (1/N of the
+    # result per rank, like the input rows it uploads). Hierarchies with an Actor or several prediction inputs use the
+    # plain step() + getPredictionCs() loop.
+    pipelined = len(pred_idx) == 1 and cfg["inputTypes"][pred_idx[0]] == InputType.prediction
+    rx0 = rx1 = 0
+    if pipelined and world > 1 and not ens:
+        X = cfg["inputSizes"][pred_idx[0]][0]
+        rx0, rx1 = rank * X // world, (rank + 1) * X // world
     w0 = time.perf_counter()
-    for t in range(burn + W, burn + W + Ke):
-        h.step([a[t] for a in host_in], True)
-        for i in pred_idx:
-            h.getPredictionCs(i)
+    if pipelined:
+        pi = pred_idx[0]
+        n_out = (cfg["inputSizes"][pi][0] if rx1 <= rx0 else rx1 - rx0) * cfg["inputSizes"][pi][1] * B
+        out_buf = np.empty(n_out, dtype=np.int32)
+        ticket = None
+        for t in range(burn + W, burn + W + Ke):
+            h.step([a[t] for a in host_in], True)
+            nxt = h.predictionReadbackQueue(pi, rx0, rx1)
+            if ticket is not None:
+                h.predictionReadbackFinish(ticket, out_buf)
+            ticket = nxt
+        h.predictionReadbackFinish(ticket, out_buf)
+    else:
+        for t in range(burn + W, burn + W + Ke):
+            h.step([a[t] for a in host_in], True)
+            for i in pred_idx:
+                h.getPredictionCs(i)
     barrier()
     e2e_s = time.perf_counter() - w0
     if dist is not None:
@@ -522,6 +544,8 @@ def main():
         x0, x1 = rank * s0[0] // world, (rank + 1) * s0[0] // world
         h2d = (max(plan[3], x1) - min(plan[2], x0)) * s0[1] * 4
     d2h = sum(cfg["inputSizes"][i][0] * cfg["inputSizes"][i][1] * 4 * B for i in pred_idx)
+    if pipelined and rx1 > rx0:
+        d2h = (rx1 - rx0) * cfg["inputSizes"][pred_idx[0]][1] * 4
     try:
         shash, scols = state_hash(h, cfg, pred_idx, rank, world, dist, ens)
     except Exception as e:  # never take the timing down with it
@@ -606,7 +630,11 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
            "higher_is_better": True, "scaling": "weak" if ens else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": config, "roofline": roofline, "cpu_baseline": cpu,
-           "e2e": {"value": Ke / e2e_s * (B * world if ens else 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+           "e2e": {"value": Ke / e2e_s * (B * world if ens else 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                   "per": "rank" if world > 1 else "job",
+                   "api": ("Hierarchy.step(host CSDR) + prediction readback pipelined one step deep (ogn_prediction_readback_queue/finish)"
+                           + ("; every rank uploads the input rows its shard reads and reads back its own slab of the prediction" if world > 1 and not ens else ""))
+                   if pipelined else "Hierarchy.step(host CSDR) + getPredictionCs() every step"},
            "gpu_launches": int(sum(n for _, n in prof.values())), "clocks": clk,
            "state_hash": {"crc32": shash, "weight_columns": scols, "after_steps": burn + W + K + Ke,
                           "covers": "prediction CSDRs, SparseCoder hidden CSDRs, 8 SparseCoder + 8 Predictor weight columns per layer; "

@@ -65,6 +65,11 @@ public:
                     bool learnEnabled, bool mimic);
     const int *hiddenCsDevice() const;
     void readFromStream(std::istream &is, ComputeSystem &cs);
+    // raw device state (weights in their device layout, history ring, hyper-parameters) of an already constructed layer of
+    // the same shape: the Actor part of Hierarchy::writeCheckpoint / readCheckpoint (Actor.cpp:315-438 is the reference's
+    // own save format, which writeToStream keeps)
+    void writeDeviceState(std::ostream &os) const;
+    void readDeviceState(std::istream &is);
 
 private:
     Int3 hiddenSize;

@@ -89,6 +89,13 @@ public:
                     float reward = 0.0f, bool mimic = false);
     // Device pointer to the prediction CSDR of input i (valid until the hierarchy is destroyed).
     const int *getPredictionCsDevice(int i) const;
+    // Pipelined readback for streaming callers: queue() copies x rows [x0, x1) of the CURRENT prediction CSDR of input i
+    // (x1 <= x0: all of it) to pinned memory on a copy stream, behind the work queued so far, and returns a ticket; finish()
+    // waits for that copy only and hands out the ints. Two tickets may be outstanding, so step t + 1 can be queued before
+    // the prediction of step t is collected. A sharded rank that asks for rows of its own slab does not wait for the
+    // exchange with the other ranks.
+    int queuePredictionReadback(int i, int x0, int x1);
+    int finishPredictionReadback(int ticket, int *out);
     // An ensemble of seeds.size() independent hierarchies of identical shape stepped in lockstep by the same kernel
     // launches (BASELINE config 5). Member k is initialised exactly like initRandom() with cs.rng.seed(seeds[k]); every
     // CSDR passed to / returned from the hierarchy then holds the members back to back ([member][columns]).
@@ -99,7 +106,9 @@ public:
     // x-slab shards: SURVEY.md §8f-1): 64-bit counts, weights streamed in their device layouts through pinned staging,
     // one file per rank. Layout: "OGNCKPT1", the initRandom arguments, ensemble size and shard (rank, world), tick state,
     // history rings, then SparseCoder / Predictor device state layer by layer. readCheckpoint rebuilds the hierarchy from
-    // the header (device-side init, then overwritten). Hierarchies with an Actor use writeToStream instead.
+    // the header (device-side init, then overwritten).
+    // Actor layers are covered (weights, history ring, hyper-parameters); ComputeSystem::rng is the caller's to carry over
+    // (ogn_checkpoint_save stores it next to the hierarchy).
     void writeCheckpoint(std::ostream &os, const std::vector<InputType> &inputTypes, const std::vector<LayerDesc> &layerDescs) const;
     void readCheckpoint(std::istream &is, ComputeSystem &cs, std::vector<InputType> *inputTypesOut = nullptr);
     void readFromStream(std::istream &is, ComputeSystem &cs); // choose the device / stream to load onto
@@ -117,6 +126,7 @@ private:
     void initImpl(ComputeSystem &cs, const std::vector<Int3> &inputSizes, const std::vector<InputType> &inputTypes,
                   const std::vector<LayerDesc> &layerDescs, int batch, int member);
     bool smallEligible(ComputeSystem &cs);
+    unsigned haloWaitMask(ComputeSystem &cs, int l);
     void stepImpl(ComputeSystem &cs, const int *const *hostIn, const std::vector<const int *> *devIn,
                   bool learnEnabled, float reward, bool mimic);
 };

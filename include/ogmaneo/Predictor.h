@@ -56,6 +56,7 @@ public:
     int smallUnits() const; // see SparseCoder::smallUnits
     void stateSignature(std::vector<int> &key) const; // everything that selects this layer's kernel arguments (graph cache key)
     void hiddenRows(int &lo, int &hi) const; // hidden x rows [lo,hi) this device owns
+    void visibleRows(int vli, int &lo, int &hi) const; // x rows of visible layer vli this device's slab reads
     int copyHiddenCs(int *out) const; // getHiddenCs() straight into out (pinned staging); returns the column count
     void initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize, const std::vector<VisibleLayerDesc> &visibleLayerDescs,
                           int batch, int member);

@@ -68,7 +68,9 @@ public:
     // the forward pass / per (visible layer, pack) of the reconstruction), or -1 if some phase has no 128-bit kernel path
     int smallUnits() const;
     void stateSignature(std::vector<int> &key) const; // everything that selects this layer's kernel arguments (graph cache key)
-    void stepDevice(ComputeSystem &cs, const int *const *inputCsDevice, bool learnEnabled, int *copyOut);
+    void stepDevice(ComputeSystem &cs, const int *const *inputCsDevice, bool learnEnabled, int *copyOut, unsigned exchangeWaitMask = 0);
+    // hidden x rows [lo, hi) of this layer's CSDR that this device's learn pass reads (owned slab + replica rows)
+    void learnRows(int &lo, int &hi) const;
     const int *hiddenCsDevice() const;
     // raw device state (weights in their device layouts, CSDRs, parities) of an already constructed layer of the same
     // shape: the building block of Hierarchy::writeCheckpoint / readCheckpoint

@@ -67,6 +67,13 @@ int ogn_checkpoint_load(const char *path, const ogn_create_options *opt, void **
 int ogn_step_device(void *h, const int *const *input_cs_dev, int learn_enabled, float reward, int mimic);
 /* Device pointer of the prediction CSDR of input i ([member][columns]); valid for the life of the handle. */
 const int *ogn_prediction_cs_device(void *h, int i);
+/* Pipelined readback of the prediction CSDR of input i for streaming callers (Hierarchy::getPredictionCs, Hierarchy.h:144-151,
+ * without stalling the queue): queue() copies x rows [x0, x1) of the CURRENT prediction (x1 <= x0: all of it) to pinned
+ * memory on a copy stream, behind the work queued so far, and returns a ticket (0 or 1; -1 on error); finish() waits for
+ * that copy only, writes the ints to out and returns their number. Two tickets may be outstanding: queue step t + 1 before
+ * collecting the prediction of step t. A shard that asks for rows of its own slab does not wait for the other ranks. */
+int ogn_prediction_readback_queue(void *h, int i, int x0, int x1);
+int ogn_prediction_readback_finish(void *h, int ticket, int *out);
 /* The cudaStream_t all work of this hierarchy is queued on / wait for it to drain. */
 void *ogn_stream(void *h);
 int ogn_synchronize(void *h);

@@ -251,14 +251,17 @@ int ogn_actor_learn(const ogn_actor_args *args_host, const ogn_actor_batch *batc
  * in THIS process (CUDA IPC); the buffer lives at the same offset in every arena. One launch: this rank's slab
  * [rank*count, (rank+1)*count) is stored into every peer's arena with 128-bit NVLink stores, the last block to finish
  * raises this rank's arrival flag (arena word `rank`, value epoch) in every peer with a system-scope release store and
- * waits until every peer's flag in the local arena reached epoch (acquire loads, bounded by timeout_ns; on timeout
- * *err_flag, a host-mapped word, is set to 1). Kernels queued behind it on the stream see the complete buffer. */
+ * waits until the flag of every peer in wait_mask (bit r = rank r) reached epoch in the local arena (acquire loads, bounded
+ * by timeout_ns; on timeout *err_flag, a host-mapped word, is set to 1). Kernels queued behind it on the stream see the
+ * slabs of the ranks waited for; with a partial mask (the x-neighbours whose halo rows the next kernels read) the other
+ * slabs are guaranteed complete only after a later exchange with the full mask: flags only grow, and a rank raises
+ * exchange k + 1 after it delivered exchange k. */
 #define OGN_MAX_PEERS 16
 typedef struct ogn_peer_table {
     int *base[OGN_MAX_PEERS];
     int rank, world;
 } ogn_peer_table;
-int ogn_peer_allgather(const ogn_peer_table *table_host, int64_t offset_ints, int count_per_rank, unsigned epoch,
+int ogn_peer_allgather(const ogn_peer_table *table_host, int64_t offset_ints, int count_per_rank, unsigned epoch, unsigned wait_mask,
                        unsigned long long timeout_ns, unsigned *err_flag, void *stream);
 
 /* Weight (re)layout between the reference's CSR value order and the device layouts, for hidden columns

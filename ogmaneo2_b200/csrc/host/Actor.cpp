@@ -338,4 +338,41 @@ void Actor::readFromStream(std::istream &is) {
 
 const int *Actor::hiddenCsDevice() const { return impl->hiddenCs.ptr(); }
 
+void Actor::writeDeviceState(std::ostream &os) const {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    const float hp[3] = {alpha, beta, gamma};
+    const int hi[5] = {minSteps, historyIters, m.capacity, m.start, m.historySize};
+    os.write(reinterpret_cast<const char *>(hp), sizeof(hp));
+    os.write(reinterpret_cast<const char *>(hi), sizeof(hi));
+    os.write(reinterpret_cast<const char *>(m.rewards.data()), (std::streamsize)(m.rewards.size() * sizeof(float)));
+    writeDev(os, ctx, m.acts); writeDev(os, ctx, m.values); writeDev(os, ctx, m.hiddenCs);
+    for (const auto &b : m.histInput) writeDev(os, ctx, b);
+    writeDev(os, ctx, m.histTarget); writeDev(os, ctx, m.histValues);
+    for (const WeightSet &w : m.vw.sets) writeDev(os, ctx, w.wf);
+    for (const WeightSet &w : m.aw.sets) writeDev(os, ctx, w.wf);
+}
+
+void Actor::readDeviceState(std::istream &is) {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    float hp[3];
+    int hi[5];
+    is.read(reinterpret_cast<char *>(hp), sizeof(hp));
+    is.read(reinterpret_cast<char *>(hi), sizeof(hi));
+    if (!is || hi[2] != m.capacity) throw std::runtime_error("ogmaneo-b200: checkpoint Actor history capacity mismatch");
+    alpha = hp[0]; beta = hp[1]; gamma = hp[2];
+    minSteps = hi[0]; historyIters = hi[1]; m.start = hi[3]; m.historySize = hi[4];
+    is.read(reinterpret_cast<char *>(m.rewards.data()), (std::streamsize)(m.rewards.size() * sizeof(float)));
+    readDev(is, ctx, m.acts); readDev(is, ctx, m.values); readDev(is, ctx, m.hiddenCs);
+    for (auto &b : m.histInput) readDev(is, ctx, b);
+    readDev(is, ctx, m.histTarget); readDev(is, ctx, m.histValues);
+    for (WeightSet &w : m.vw.sets) readDev(is, ctx, w.wf);
+    for (WeightSet &w : m.aw.sets) readDev(is, ctx, w.wf);
+    m.csDirty = m.valDirty = true;
+    std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
+}
+
 } // namespace ogmaneo

@@ -124,7 +124,7 @@ void DeviceContext::arenaAttach(const void *handles64, int world) {
     arena->attached = true;
 }
 
-void DeviceContext::peerAllGather(int *buffer, int countPerRank, bool deferred) {
+void DeviceContext::peerAllGather(int *buffer, int countPerRank, bool deferred, unsigned waitMask) {
     PeerArena &a = *arena;
     deferred = deferred && useSide;
     // exchanges complete in the same order on every rank: an earlier deferred one is joined before the next is queued
@@ -141,7 +141,10 @@ void DeviceContext::peerAllGather(int *buffer, int countPerRank, bool deferred) 
         const char *e = std::getenv("OGN_PEER_TIMEOUT_MS");
         return (unsigned long long)(e ? std::atoll(e) : 5000) * 1000000ull;
     }();
-    kernelCheck(ogn_peer_allgather(&t, buffer - a.base, countPerRank, ++a.epoch, timeoutNs, a.errDev, st), "peer_allgather");
+    const unsigned everybody = (a.world >= 32 ? 0xffffffffu : ((1u << a.world) - 1u)) & ~(1u << a.rank);
+    static const bool haloWait = [] { const char *e = std::getenv("OGN_PEER_HALO_WAIT"); return !e || std::atoi(e) != 0; }();
+    const unsigned mask = (waitMask && haloWait) ? (waitMask & everybody) : everybody;
+    kernelCheck(ogn_peer_allgather(&t, buffer - a.base, countPerRank, ++a.epoch, mask, timeoutNs, a.errDev, st), "peer_allgather");
     if (deferred) exchangeQueued();
 }
 

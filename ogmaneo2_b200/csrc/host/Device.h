@@ -68,7 +68,9 @@ struct DeviceContext {
     void arenaAttach(const void *handles64, int world);
     // in-place all-gather of [world][countPerRank] ints on `stream`; deferred = queue it on the side stream instead (the
     // step's final output: nothing on `stream` needs it before the next exchange, which joins it)
-    void peerAllGather(int *buffer, int countPerRank, bool deferred = false);
+    // waitMask: ranks whose slabs the kernels queued next read (0 = everybody); a partial mask requires that an exchange
+    // with the full mask follows before anything reads the other slabs
+    void peerAllGather(int *buffer, int countPerRank, bool deferred = false, unsigned waitMask = 0);
     void peerCheck() const;                              // throws if a peer wait timed out
     unsigned long long peerTakeWaitNs();                 // device time spent waiting for other ranks since the last call (syncs)
     // Side stream: SparseCoder learn (reconstruction + update) of a step runs here, concurrently with the Predictors on

@@ -124,6 +124,16 @@ const int *ogn_prediction_cs_device(void *hh, int i) {
     guard([&] { p = ((Handle *)hh)->h.getPredictionCsDevice(i); });
     return p;
 }
+int ogn_prediction_readback_queue(void *hh, int i, int x0, int x1) {
+    int t = -1;
+    guard([&] { t = ((Handle *)hh)->h.queuePredictionReadback(i, x0, x1); });
+    return t;
+}
+int ogn_prediction_readback_finish(void *hh, int ticket, int *out) {
+    int n = -1;
+    guard([&] { n = ((Handle *)hh)->h.finishPredictionReadback(ticket, out); });
+    return n;
+}
 int ogn_ensemble_size(void *hh) { return ((Handle *)hh)->h.getEnsembleSize(); }
 uint64_t ogn_take_sc_update_count(void *hh, int l) {
     uint64_t v = 0;
@@ -259,6 +269,9 @@ int64_t ogn_checkpoint_save(void *h, const char *path) {
         std::ofstream os(path, std::ios::binary);
         if (!os) throw std::runtime_error("cannot open file for writing");
         H->h.writeCheckpoint(os, H->types, H->lds);
+        // trailer: the ComputeSystem's generator (Actor sampling and history draws continue from it), libstdc++ text form
+        os.write("OGNRNG1\n", 8);
+        os << H->cs.rng << "\n";
         n = (int64_t)os.tellp();
     });
     return n;
@@ -277,6 +290,12 @@ int ogn_checkpoint_load(const char *path, const ogn_create_options *opt, void **
             H->cs.peerExchange = opt->peer_exchange != 0;
         }
         H->h.readCheckpoint(is, H->cs, &H->types);
+        {   // optional trailer with the generator state (files written before it existed simply end here)
+            char tag[8] = {0};
+            is.read(tag, 8);
+            if (is && std::memcmp(tag, "OGNRNG1\n", 8) == 0) is >> H->cs.rng;
+            is.clear();
+        }
         // the layer descriptors travel in the file; keep them so that the handle can be checkpointed again
         const int L = H->h.getNumLayers();
         H->lds.resize(L);

@@ -49,12 +49,22 @@ struct Hierarchy::Impl {
             if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
         graphs.clear();
     }
+    // pipelined prediction readback (queuePredictionReadback): two pinned slots on a copy stream of their own
+    struct Readback { PinnedBuf<int> buf; cudaEvent_t done = nullptr; size_t n = 0; bool pending = false; };
+    Readback rb[2];
+    int rbNext = 0;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t rbSrcReady = nullptr;
     std::vector<std::vector<Ring>> histories; // [layer][input]
     std::vector<std::unique_ptr<PinnedBuf<int>>> inPinned;
     cudaEvent_t inFree = nullptr; // pinned input staging may be overwritten after this event
     ~Impl() {
         dropGraphs();
         if (inFree) cudaEventDestroy(inFree);
+        for (auto &r : rb)
+            if (r.done) cudaEventDestroy(r.done);
+        if (rbSrcReady) cudaEventDestroy(rbSrcReady);
+        if (copyStream) cudaStreamDestroy(copyStream);
     }
 };
 
@@ -193,6 +203,31 @@ void Hierarchy::initRandomEnsemble(ComputeSystem &cs, const std::vector<unsigned
 
 int Hierarchy::getEnsembleSize() const { return impl ? impl->batch : 0; }
 
+// Sharded top layer: the kernels queued behind the exchange of its hidden CSDR (its own learn pass, the Predictors of
+// the layer) read only rows near this device's slab, so the exchange waits for the ranks owning those rows instead of for
+// everybody. Requires a later exchange of the same step that does wait for everybody (the deferred exchange of the
+// layer-0 predictions), which is what makes the other slabs complete for getters. 0 = wait for everybody.
+unsigned Hierarchy::haloWaitMask(ComputeSystem &cs, int l) {
+    if (cs.shardWorld <= 1 || l != (int)scLayers.size() - 1) return 0;
+    bool finalExchange = false;
+    for (auto &p : pLayers[0]) finalExchange = finalExchange || p != nullptr;
+    if (!finalExchange) return 0;
+    int lo = 0, hi = 0;
+    scLayers[l].learnRows(lo, hi);
+    for (auto &p : pLayers[l]) {
+        if (!p) continue;
+        int a = 0, b = 0;
+        p->visibleRows(0, a, b); // visible layer 0 of a Predictor is this layer's hidden CSDR
+        lo = std::min(lo, a); hi = std::max(hi, b);
+    }
+    const int Hx = scLayers[l].getHiddenSize().x, rows = Hx / cs.shardWorld;
+    if (rows <= 0 || hi <= lo) return 0;
+    unsigned mask = 0;
+    for (int r = 0; r < cs.shardWorld && r < 32; r++)
+        if (r != cs.shardRank && r * rows < hi && (r + 1) * rows > lo) mask |= 1u << r;
+    return mask ? mask : 0;
+}
+
 // Whether this hierarchy steps through the single-launch kernel, and with which launch shape (decided once).
 bool Hierarchy::smallEligible(ComputeSystem &cs) {
     Impl &m = *impl;
@@ -247,6 +282,9 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
 
     ctx.beginStep();
     ticks[0] = 0;
+    // a queued prediction readback still reads the buffer this step's Predictor will overwrite
+    for (auto &r : m.rb)
+        if (r.pending) cudaCheck(cudaStreamWaitEvent(ctx.stream, r.done, 0), "cudaStreamWaitEvent");
     const bool small = smallEligible(cs);
     ogn_small_inputs smallIn;
     std::memset(&smallIn, 0, sizeof(smallIn));
@@ -314,7 +352,7 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
             copyOut = m.histories[l + 1][0].slot(0);
         }
         if (ctx.collect) ctx.collect->curLayer = l;
-        scLayers[l].stepDevice(cs, ptrs.data(), learnEnabled, copyOut);
+        scLayers[l].stepDevice(cs, ptrs.data(), learnEnabled, copyOut, haloWaitMask(cs, l));
         if (l < L - 1) {
             consumeKernel1(cs, scLayers[l].getHiddenSize().x * scLayers[l].getHiddenSize().y);
             ticks[l + 1]++;
@@ -475,6 +513,52 @@ const int *Hierarchy::getPredictionCsDevice(int i) const {
     if (impl) impl->ctx->joinExchange();
     if (aLayers[i] != nullptr) return aLayers[i]->hiddenCsDevice();
     return pLayers.front()[i]->hiddenCsDevice();
+}
+
+int Hierarchy::queuePredictionReadback(int i, int x0, int x1) {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    if (aLayers[i] != nullptr || !pLayers.front()[i]) throw std::invalid_argument("ogmaneo-b200: readback needs a prediction input");
+    Predictor &p = *pLayers.front()[i];
+    const int X = p.getHiddenSize().x, Y = p.getHiddenSize().y;
+    size_t off = 0, n = (size_t)X * Y * m.batch;
+    bool own = false;
+    if (x1 > x0) {
+        if (m.batch > 1 || x0 < 0 || x1 > X) throw std::invalid_argument("ogmaneo-b200: readback row range");
+        off = (size_t)x0 * Y; n = (size_t)(x1 - x0) * Y;
+        int a = 0, b = 0;
+        p.hiddenRows(a, b);
+        own = x0 >= a && x1 <= b;
+    }
+    if (!own) ctx.joinExchange(); // rows of other ranks arrive with the deferred exchange
+    if (!m.copyStream) {
+        cudaCheck(cudaStreamCreateWithFlags(&m.copyStream, cudaStreamNonBlocking), "cudaStreamCreate");
+        cudaCheck(cudaEventCreateWithFlags(&m.rbSrcReady, cudaEventDisableTiming), "cudaEventCreate");
+    }
+    const int t = m.rbNext;
+    Impl::Readback &r = m.rb[t];
+    if (r.pending) throw std::runtime_error("ogmaneo-b200: two prediction readbacks are already outstanding");
+    if (!r.done) cudaCheck(cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming), "cudaEventCreate");
+    if (r.buf.size() < n) r.buf.alloc(n);
+    cudaCheck(cudaEventRecord(m.rbSrcReady, ctx.stream), "cudaEventRecord");
+    cudaCheck(cudaStreamWaitEvent(m.copyStream, m.rbSrcReady, 0), "cudaStreamWaitEvent");
+    cudaCheck(cudaMemcpyAsync(r.buf.ptr(), p.hiddenCsDevice() + off, n * sizeof(int), cudaMemcpyDeviceToHost, m.copyStream), "prediction D2H");
+    cudaCheck(cudaEventRecord(r.done, m.copyStream), "cudaEventRecord");
+    r.n = n; r.pending = true;
+    m.rbNext = 1 - t;
+    return t;
+}
+
+int Hierarchy::finishPredictionReadback(int ticket, int *out) {
+    Impl &m = *impl;
+    if (ticket < 0 || ticket > 1 || !m.rb[ticket].pending) throw std::invalid_argument("ogmaneo-b200: no such readback ticket");
+    Impl::Readback &r = m.rb[ticket];
+    cudaCheck(cudaEventSynchronize(r.done), "cudaEventSynchronize");
+    m.ctx->peerCheck();
+    if (out) std::memcpy(out, r.buf.ptr(), r.n * sizeof(int));
+    r.pending = false;
+    return (int)r.n;
 }
 
 // --- state ---------------------------------------------------------------------------------------------------------
@@ -650,8 +734,6 @@ void Hierarchy::writeCheckpoint(std::ostream &os, const std::vector<InputType> &
     const Impl &m = *impl;
     DeviceContext &ctx = *m.ctx;
     cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
-    for (auto &a : aLayers)
-        if (a) throw std::runtime_error("ogmaneo-b200: checkpoints do not cover Actor layers (use writeToStream)");
     const int L = (int)scLayers.size(), NI = (int)inputSizes.size();
     if ((int)inputTypes.size() != NI || (int)lds.size() != L) throw std::invalid_argument("ogmaneo-b200: checkpoint descriptors do not match");
     os.write(kCkptMagic, sizeof(kCkptMagic));
@@ -671,6 +753,8 @@ void Hierarchy::writeCheckpoint(std::ostream &os, const std::vector<InputType> &
         for (auto &p : pLayers[l])
             if (p) p->writeDeviceState(os);
     }
+    for (auto &a : aLayers)
+        if (a) a->writeDeviceState(os);
     if (!os) throw std::runtime_error("ogmaneo-b200: checkpoint write failed");
 }
 
@@ -716,6 +800,8 @@ void Hierarchy::readCheckpoint(std::istream &is, ComputeSystem &cs, std::vector<
         for (auto &p : pLayers[l])
             if (p) p->readDeviceState(is);
     }
+    for (auto &a : aLayers)
+        if (a) a->readDeviceState(is);
     if (typesOut) *typesOut = types;
 }
 

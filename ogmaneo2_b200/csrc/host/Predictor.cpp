@@ -171,6 +171,7 @@ const IntBuffer &Predictor::getHiddenCs() const {
 }
 
 void Predictor::hiddenRows(int &lo, int &hi) const { lo = impl->x0; hi = impl->x1; }
+void Predictor::visibleRows(int vli, int &lo, int &hi) const { lo = impl->ws.sets[vli].vx0; hi = impl->ws.sets[vli].vx1; }
 
 int Predictor::copyHiddenCs(int *out) const {
     Impl &m = *impl;

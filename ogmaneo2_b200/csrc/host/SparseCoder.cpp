@@ -84,7 +84,7 @@ void SparseCoder::initRandomMember(ComputeSystem &cs, const Int3 &hiddenSize_, c
 }
 
 // SparseCoder.cpp:127-147 with device-resident inputs. copyOut (optional) receives hiddenCs too (next layer's history).
-void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bool learnEnabled, int *copyOut) {
+void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bool learnEnabled, int *copyOut, unsigned exchangeWaitMask) {
     Impl &m = *impl;
     DeviceContext &ctx = *m.ctx;
     const int nvl = (int)visibleLayerDescs.size();
@@ -121,7 +121,7 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
     if (!ctx.dry) kernelCheck(ogn_sc_forward(&fa, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, out, sharded ? nullptr : copyOut,
                                ctx.stream), "sc_forward"); }
     if (sharded) {
-        if (ctx.arena && ctx.inArena(out)) ctx.peerAllGather(out, (m.x1 - m.x0) * hiddenSize.y);
+        if (ctx.arena && ctx.inArena(out)) ctx.peerAllGather(out, (m.x1 - m.x0) * hiddenSize.y, false, copyOut ? 0u : exchangeWaitMask);
         else if (cs.allGather) cs.allGather(cs.allGatherUser, out, (m.x1 - m.x0) * hiddenSize.y, (void *)ctx.stream);
         else throw std::runtime_error("ogmaneo-b200: shardWorld > 1 needs ComputeSystem::allGather or peerExchange");
         if (copyOut)
@@ -352,6 +352,10 @@ void SparseCoder::setHiddenState(const IntBuffer &hc, const IntBuffer &hcPrev) {
 
 const int *SparseCoder::hiddenCsDevice() const { return impl->cs_[impl->cur].ptr(); }
 
+void SparseCoder::learnRows(int &lo, int &hi) const {
+    lo = impl->x0; hi = impl->x1;
+    for (const WeightSet &w : impl->ws.sets) { lo = std::min(lo, w.rx0); hi = std::max(hi, w.rx1); }
+}
 void SparseCoder::visibleRows(int vli, int &lo, int &hi) const { lo = impl->ws.sets[vli].vx0; hi = impl->ws.sets[vli].vx1; }
 int SparseCoder::shardRank() const { return impl->rank; }
 int SparseCoder::shardWorld() const { return impl->world; }

@@ -798,8 +798,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 __global__ void __launch_bounds__(256)
-k_peer_allgather(const __grid_constant__ ogn_peer_table T, long long off, int count, unsigned epoch, unsigned long long timeoutNs,
-                 unsigned *errFlag) {
+k_peer_allgather(const __grid_constant__ ogn_peer_table T, long long off, int count, unsigned epoch, unsigned waitMask,
+                 unsigned long long timeoutNs, unsigned *errFlag) {
     __shared__ int lastBlock;
     if (T.world > 1 && count > 0) {
         int p = blockIdx.y;
@@ -827,7 +827,9 @@ k_peer_allgather(const __grid_constant__ ogn_peer_table T, long long off, int co
         st_release_sys(reinterpret_cast<unsigned *>(T.base[q]) + T.rank, epoch); // "rank has delivered exchange #epoch" in q's arena
         const unsigned long long t0 = global_ns();
         unsigned long long t1 = t0;
-        while ((int)(ld_acquire_sys(hdr + q) - epoch) < 0) {
+        // every peer gets the slab and the flag; only the ranks in waitMask are waited for (the ones whose rows the kernels
+        // queued behind this exchange read). The other slabs are complete once a later exchange that waits for everybody is.
+        while (((waitMask >> q) & 1u) && (int)(ld_acquire_sys(hdr + q) - epoch) < 0) {
             t1 = global_ns();
             if (t1 - t0 > timeoutNs) { *errFlag = 1u; break; }
         }
@@ -1194,7 +1196,7 @@ int ogn_actor_learn(const ogn_actor_args *args, const ogn_actor_batch *batch, in
     return launch_status();
 }
 
-int ogn_peer_allgather(const ogn_peer_table *table, int64_t offset_ints, int count_per_rank, unsigned epoch,
+int ogn_peer_allgather(const ogn_peer_table *table, int64_t offset_ints, int count_per_rank, unsigned epoch, unsigned wait_mask,
                        unsigned long long timeout_ns, unsigned *err_flag, void *stream) {
     if (table->world <= 1) return 0;
     if (table->world > OGN_MAX_PEERS || table->rank < 0 || table->rank >= table->world) return (int)cudaErrorInvalidValue;
@@ -1202,7 +1204,7 @@ int ogn_peer_allgather(const ogn_peer_table *table, int64_t offset_ints, int cou
     if (bx < 1) bx = 1;
     if (bx > 16) bx = 16;
     dim3 grid((unsigned)bx, (unsigned)(table->world - 1));
-    k_peer_allgather<<<grid, 256, 0, (cudaStream_t)stream>>>(*table, offset_ints, count_per_rank, epoch, timeout_ns, err_flag);
+    k_peer_allgather<<<grid, 256, 0, (cudaStream_t)stream>>>(*table, offset_ints, count_per_rank, epoch, wait_mask, timeout_ns, err_flag);
     return launch_status();
 }
 

@@ -42,6 +42,8 @@ _PRODUCT_SIGS = {
     "step_device": (C.c_int, [_VP, C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_int]),
     "prediction_cs_device": (C.c_void_p, [_VP, C.c_int]),
     "stream": (C.c_void_p, [_VP]),
+    "prediction_readback_queue": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int]),
+    "prediction_readback_finish": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_int)]),
     "synchronize": (C.c_int, [_VP]),
     "ensemble_size": (C.c_int, [_VP]),
     "take_sc_update_count": (C.c_uint64, [_VP, C.c_int]),
@@ -167,6 +169,19 @@ class Hierarchy(FlatHierarchy):
 
     def predictionCsDevice(self, i: int) -> int:
         return int(self.f.prediction_cs_device(self.h, i) or 0)
+
+    def predictionReadbackQueue(self, i: int, x0: int = 0, x1: int = 0) -> int:
+        """Queue an asynchronous copy of x rows [x0, x1) (default: all) of the current prediction of input i; returns a ticket."""
+        t = int(self.f.prediction_readback_queue(self.h, i, x0, x1))
+        if t < 0:
+            raise RuntimeError(f"ogn_prediction_readback_queue failed: {self.f.error()}")
+        return t
+
+    def predictionReadbackFinish(self, ticket: int, out: np.ndarray) -> int:
+        n = int(self.f.prediction_readback_finish(self.h, ticket, out.ctypes.data_as(C.POINTER(C.c_int))))
+        if n < 0:
+            raise RuntimeError(f"ogn_prediction_readback_finish failed: {self.f.error()}")
+        return n
 
     def stream(self) -> int:
         return int(self.f.stream(self.h) or 0)

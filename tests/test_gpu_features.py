@@ -345,3 +345,51 @@ def test_checkpoint_round_trip(product, tmp_path, ensemble):
     pa, pb = str(tmp_path / "a2.ckpt"), str(tmp_path / "b2.ckpt")
     a.checkpointSave(pa); b.checkpointSave(pb)
     assert zlib.crc32(open(pa, "rb").read()) == zlib.crc32(open(pb, "rb").read())
+
+
+def test_checkpoint_round_trip_with_actor(product, tmp_path):
+    """The 64-bit checkpoint covers Actor layers (weights, history ring, hyper-parameters) and the ComputeSystem generator:
+    a restored Actor hierarchy samples the same actions and learns the same weights as the one that wrote the file."""
+    from common import reward_at
+    cfg = configs.c3_actor(8)
+    a = product.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=cfg["seed"])
+    a.setActorParams(1, 0.03, 0.015, 0.97, 5, 6)
+    action = None
+    for t in range(31):
+        a.step(make_inputs(cfg, t, action), True, reward_at(t))
+        action = a.getPredictionCs(1)
+    path = str(tmp_path / "actor.ckpt")
+    assert a.checkpointSave(path) > 0
+    b = product.Hierarchy.checkpointLoad(path, cfg["inputSizes"])
+    act_b = action
+    for t in range(31, 60):
+        a.step(make_inputs(cfg, t, action), True, reward_at(t))
+        b.step(make_inputs(cfg, t, act_b), True, reward_at(t))
+        action, act_b = a.getPredictionCs(1), b.getPredictionCs(1)
+        assert np.array_equal(action, act_b), f"restored Actor picks different actions at step {t}"
+    d = diff_snapshots(a.snapshot(True), b.snapshot(True))
+    assert not d, d[:3]
+    assert a.rngPeek() == b.rngPeek()
+
+
+def test_pipelined_prediction_readback(product):
+    """ogn_prediction_readback_queue / finish: the prediction of step t collected after step t + 1 was queued equals
+    getPredictionCs() right after step t; a row range returns exactly those rows."""
+    cfg = configs.c2_video(10, 2)
+    a = product.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=3)
+    b = product.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=3)
+    want, out, prev = [], np.empty(100, np.int32), None
+    for t in range(12):
+        ins = make_inputs(cfg, t)
+        a.step(ins, True)
+        want.append(a.getPredictionCs(0))
+        b.step(ins, True)
+        tk = b.predictionReadbackQueue(0)
+        if prev is not None:
+            assert b.predictionReadbackFinish(prev[0], out) == 100
+            assert np.array_equal(out, want[prev[1]]), f"pipelined readback of step {prev[1]} differs"
+        prev = (tk, t)
+    assert b.predictionReadbackFinish(prev[0], out) == 100 and np.array_equal(out, want[-1])
+    rows = np.empty(30, np.int32)
+    tk = b.predictionReadbackQueue(0, 2, 5)
+    assert b.predictionReadbackFinish(tk, rows) == 30 and np.array_equal(rows, want[-1].reshape(10, 10)[2:5].reshape(-1))
