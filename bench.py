@@ -198,6 +198,38 @@ class _DevArray:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def time_cpu_members(members, steps, warmup, budget_s):
+    """C5: `members` independent hierarchies (seed 1234 + k, stream shifted by 17 k) stepped one after the other by the
+    reference with all host threads; returns (member-steps/s, info)."""
+    from oracle import loader
+    flat, kind = loader.best()
+    cores = os.cpu_count() or 1
+    flat.set_num_threads(cores)
+    total_steps, total_t, t_init = 0, 0.0, 0.0
+    for k in range(members):
+        c = configs.c5_unit(16, k)
+        t0 = time.perf_counter()
+        h = FlatHierarchy(flat, c["inputSizes"], c["inputTypes"], c["layerDescs"], c["seed"])
+        t_init += time.perf_counter() - t0
+        ins = [[streams.make("noisy", t, c["inputSizes"][0], seed=c["noise_seed"], shift=c["shift"])] for t in range(warmup + steps)]
+        for t in range(warmup):
+            h.step(ins[t], True)
+        t0 = time.perf_counter()
+        done = 0
+        for t in range(warmup, warmup + steps):
+            h.step(ins[t], True)
+            done += 1
+            if time.perf_counter() - t0 > budget_s / members:
+                break
+        total_t += time.perf_counter() - t0
+        total_steps += done
+        h.close()
+    v = total_steps / total_t
+    return v, {"kind": kind, "cores": cores, "sample": f"C5: {members} hierarchies (seeds 1234+k) stepped one after the other, {total_steps} "
+               f"member-steps in {total_t:.2f}s after {warmup} warm-up steps each (init {t_init:.1f}s); an ensemble of B members costs B x this",
+               "sample_steps_per_s": v}
+
+
 def time_cpu(cfg_sample, steps, warmup, full_cols, budget_s=25.0, want_trace=False):
     """The reference's CPU implementation on a bounded sample; returns (full-workload steps/s, info dict[, trace])."""
     from oracle import loader
@@ -330,12 +362,20 @@ def main():
                     help="N > 1: CSDR slab exchange by the library's peer-memory kernel (default) or NCCL all-gather")
     ap.add_argument("--ensemble", type=int, default=512, help="c5 only: hierarchies per GPU (weak scaling; 512 = 80 GB)")
     ap.add_argument("--size", type=int, default=None, help="c4 only: grid edge (default 512); smaller sizes are for profiling runs")
+    ap.add_argument("--cpu-size", type=int, default=None,
+                    help="c4 only: grid edge of the CPU sample the reference is timed on (default 128; 224 is the largest size the "
+                         "reference can construct and needs ~45 GiB of host memory and two minutes of init)")
+    ap.add_argument("--cpu-members", type=int, default=8, help="c5 only: hierarchies the reference steps for the CPU sample")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = workload(args.workload, args.gpus, args.size)
+    if args.cpu_size and args.workload == "c4":
+        cfg["sample"] = configs.c4_large(args.cpu_size)
+    if args.workload == "c5":
+        cfg["sample_members"] = max(1, args.cpu_members)
     full_cols = cfg["layerDescs"][0].hiddenSize[0] * cfg["layerDescs"][0].hiddenSize[1]
     config = {"workload": cfg["desc"], "stream": args.stream, "weights": "fp32, random init", "learn": True}
 
@@ -345,7 +385,10 @@ def main():
             return
         K = args.steps if args.steps is not None else 10
         W = args.warmup if args.warmup is not None else 3
-        value, info = time_cpu(cfg["sample"], max(K, 40) if args.workload == "c4" else K, W, full_cols, budget_s=60.0)
+        if args.workload == "c5":
+            value, info = time_cpu_members(cfg["sample_members"], max(K, 20), W, budget_s=60.0)
+        else:
+            value, info = time_cpu(cfg["sample"], max(K, 40) if args.workload == "c4" else K, W, full_cols, budget_s=60.0)
         info["value"] = value
         info["unit"] = UNIT
         same = cfg["sample"]["name"] == cfg["name"]
@@ -606,7 +649,11 @@ def main():
     cpu = None
     if not args.no_cpu and args.gpus == 1:
         try:
-            v, info, trace = time_cpu(cfg["sample"], 60 if args.workload == "c4" else 10, 1, full_cols, budget_s=12.0, want_trace=True)
+            if ens:
+                v, info = time_cpu_members(cfg["sample_members"], 10, 1, budget_s=12.0)
+                trace = None
+            else:
+                v, info, trace = time_cpu(cfg["sample"], 60 if args.workload == "c4" else 10, 1, full_cols, budget_s=12.0, want_trace=True)
             info["value"], info["unit"] = v, UNIT
             cpu = info
             if trace is not None and not ens:

@@ -162,6 +162,7 @@ typedef struct ogn_small_phase {
     int npacks, ppr;          /* packs per member and per grid row */
     int learn, activate;      /* Predictor */
     int updVer, chunks;       /* update: kernel version (1 | 2) and work units per list entry */
+    int updBatches;           /* update version 2: batches of 4 pairs per work unit */
     float alpha;
     int *out0, *out1;         /* forward: hiddenCs + optional copy; Predictor: hiddenCs */
     const int *target;        /* Predictor learn target */
@@ -187,6 +188,7 @@ int ogn_vec_geo_ok(const ogn_rf *rf_host);
  * the work units per list entry for that version */
 int ogn_sc_update_version(const ogn_learn_args *args_host);
 int ogn_sc_update_chunks(const ogn_learn_args *args_host, int version);
+int ogn_sc_update_batches(void); /* version 2: batches of 4 pairs one work unit rewrites (OGN_UPD2_BATCHES, default 4) */
 
 /* The whole step of a small hierarchy in ONE launch (SURVEY.md 8(b2) ogn_hier_step_small; replaces the ~54 runKernelN
  * fork/joins of Hierarchy::step, Hierarchy.cpp:219-284, Helpers.cpp:15-72): the phases (device array) run in order

@@ -82,7 +82,7 @@ struct DeviceContext {
     bool learnPending = false, exchangePending = false, useSide = true;
     // graphs: Hierarchy::step may capture its kernel sequence into CUDA graphs (OGN_GRAPHS=0 disables). dry: the step's
     // host code runs for its state transitions only, nothing is queued (the captured graph is launched instead).
-    bool graphs = true, dry = false;
+    bool graphs = true, dry = false, dryUncounted = false;
     // non-null: layers append the phases they would launch to this plan (and launch nothing), see SmallPlan
     SmallPlan *collect = nullptr;
     bool small = true;      // OGN_SMALL_KERNEL=0 disables the single-launch path for small hierarchies
@@ -125,6 +125,7 @@ struct LaunchScope {
     cudaStream_t st;
     cudaEvent_t a = nullptr;
     LaunchScope(DeviceContext &ctx, int kind_, cudaStream_t stream = nullptr) : c(ctx), kind(kind_), st(stream ? stream : ctx.stream) {
+        if (c.dry && c.dryUncounted) return; // the single-launch step replays host state only: nothing of this kind runs
         c.launches[kind]++;
         if (c.profiling && c.sampleThis) { a = c.takeEvent(); cudaCheck(cudaEventRecord(a, st), "cudaEventRecord"); }
     }

@@ -434,9 +434,9 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
             cudaCheck(cudaStreamSynchronize(ctx.stream), "cudaStreamSynchronize"); // `ph` is pageable and goes out of scope
             ss.nphases = (int)ph.size();
         } else {
-            ctx.dry = true;
-            try { body(); } catch (...) { ctx.dry = false; throw; }
-            ctx.dry = false;
+            ctx.dry = true; ctx.dryUncounted = true;
+            try { body(); } catch (...) { ctx.dry = false; ctx.dryUncounted = false; throw; }
+            ctx.dry = false; ctx.dryUncounted = false;
         }
         LaunchScope ls(ctx, kHierSmall);
         kernelCheck(ogn_hier_step_small(ss.phases.ptr(), ss.nphases, &smallIn, m.batch, m.smallBlocks, m.smallThreads, m.smallWide,

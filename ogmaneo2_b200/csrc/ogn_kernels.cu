@@ -1001,9 +1001,14 @@ int ogn_sc_update_version(const ogn_learn_args *args) {
     if (forced == 2) return v2ok ? 2 : 1;
     return v2ok ? 2 : 1;
 }
+int ogn_sc_update_batches(void) {
+    static int b = -1;
+    if (b < 0) { b = env_int("OGN_UPD2_BATCHES", 4); if (b < 1) b = 1; }
+    return b;
+}
 int ogn_sc_update_chunks(const ogn_learn_args *args, int version) {
     const int Vz = args->geo.Vz;
-    const int items = version == 2 ? ((2 * Vz >= 32 ? 1 : 32 / (2 * Vz)) * 4) : (32 / (Vz / 4)) * 4;
+    const int items = version == 2 ? ((2 * Vz >= 32 ? 1 : 32 / (2 * Vz)) * 4) * ogn_sc_update_batches() : (32 / (Vz / 4)) * 4;
     return (args->geo.max_cov + items - 1) / items;
 }
 
@@ -1088,10 +1093,11 @@ int ogn_sc_learn(const ogn_learn_args *args, const int *hidden_cs, const int *hi
         if (blocks > update_grid_blocks()) blocks = update_grid_blocks();
         if (ver == 2) {
             OGN_DISPATCH_Z(Vz, (vec::k_sc_update_v<Z, 2><<<(unsigned)blocks, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, work, cnt,
-                                                                                             cnt + 1, alpha, update_count, chunks)));
+                                                                                             cnt + 1, alpha, update_count, chunks,
+                                                                                             ogn_sc_update_batches())));
         } else {
             OGN_DISPATCH_Z(Vz, (vec::k_sc_update_v<Z, 1><<<(unsigned)blocks, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, work, cnt,
-                                                                                             cnt + 1, alpha, update_count, chunks)));
+                                                                                             cnt + 1, alpha, update_count, chunks, 1)));
         }
         return launch_status();
     }

@@ -541,7 +541,7 @@ __device__ __forceinline__ int sc_update_unit_v1(const ogn_learn_args &A, const 
 // the group's unchanged cells, which are bit-identical in both copies (invariant checked by ogn_weights_fr_mismatch).
 template <int Z, class CS, bool kCg>
 __device__ __forceinline__ int sc_update_unit_v2(const ogn_learn_args &A, const int *hcsAll, const int *hcsPrevAll, const int2 wk, int k0,
-                                                 float alpha) {
+                                                 int batches, float alpha) {
     constexpr int LC = Z / 4, SL = 8 * LC, PPI = SL >= 32 ? 1 : 32 / SL, J = SL >= 32 ? SL / 32 : 1, PR = 32 / Z, UN = 4;
     const ogn_rf &rf = A.geo;
     const int lane = threadIdx.x & 31;
@@ -567,39 +567,7 @@ __device__ __forceinline__ int sc_update_unit_v2(const ogn_learn_args &A, const 
         const int sl = (PPI > 1 ? lane % SL : lane) + 32 * j;
         hz8[j] = sl / LC; q4[j] = (sl % LC) * 4;
     }
-    long long offR[UN], offF[UN];
-    int fl[UN], hcl[UN];
-    float4 w[UN][J];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-        const int k = k0 + u * PPI + pi;
-        fl[u] = 0; hcl[u] = 0; offR[u] = 0; offF[u] = 0;
-        if (k < ncov) {
-            const int ox = hx0 + k / ncy, oy = hy0 + k % ncy;
-            const int h = ox * rf.Hy + oy;
-            const int hc = CS::ld(hcs + h);
-            if (hc != CS::ld(hcsPrev + h)) {
-                const int ylo = __ldg(rf.loy + oy);
-                const int dx = vx - __ldg(rf.lox + ox);
-                const int g8 = hc & ~7;
-                // R row of hidden cell g8 (the group's first), this visible column; consecutive hidden cells: + PR * Z floats
-                offR[u] = r_block(rf, ox, oy) +
-                          ((((long long)dx * __ldg(rf.ngr + oy) + (vy / PR - ylo / PR)) * rf.Hz + g8) * PR + (vy % PR)) * Z;
-                const int qh = oy / rf.pf, ph = oy % rf.pf;
-                // F: forward row of visible cell 0, hidden cell g8; consecutive visible cells: + fstep floats
-                offF[u] = f_block(rf, ox, qh) +
-                          (((long long)dx * __ldg(rf.nyf + qh) + (vy - __ldg(rf.loyf + qh))) * Z * rf.pf + ph) * rf.Hz + g8;
-                fl[u] = 1 | ((ox >= A.fx0 && ox < A.fx1) ? 2 : 0);
-                hcl[u] = hc & 7;
-            }
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u)
-#pragma unroll
-        for (int j = 0; j < J; ++j)
-            if (fl[u]) w[u][j] = ld_plain(wrm + offR[u] + (long long)hz8[j] * (PR * Z) + q4[j]);
-    // delta of the visible cells of this lane's slices (SparseCoder.cpp:78) while the loads are in flight
+    // delta of the visible cells of this lane's slices (SparseCoder.cpp:78): once per unit, shared by all its pairs
     const int target = CS::ld(vl.cs + vcol);
     float4 delta[J];
 #pragma unroll
@@ -611,27 +579,63 @@ __device__ __forceinline__ int sc_update_unit_v2(const ogn_learn_args &A, const 
         delta[j].w = alpha * ((q4[j] + 3 == target ? 1.0f : 0.0f) - ogn_expf(r.w));
     }
     int nupd = 0;
+    for (int b = 0; b < batches; ++b) {
+        const int kb = k0 + b * (UN * PPI);
+        if (kb >= ncov) break;
+        long long offR[UN], offF[UN];
+        int fl[UN], hcl[UN];
+        float4 w[UN][J];
 #pragma unroll
-    for (int u = 0; u < UN; ++u)
-        if (fl[u]) {
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                float4 nw = w[u][j];
-                if (hz8[j] == hcl[u]) {
-                    nw.x += delta[j].x; nw.y += delta[j].y; nw.z += delta[j].z; nw.w += delta[j].w;
-                    st_plain(wrm + offR[u] + (long long)hz8[j] * (PR * Z) + q4[j], nw);
-                    if (q4[j] == 0) nupd++;
-                }
-                if (fl[u] & 2) {
-                    float *f = wfm + offF[u] + (long long)q4[j] * fstep + hz8[j];
-                    f[0] = nw.x; f[fstep] = nw.y; f[2 * fstep] = nw.z; f[3 * fstep] = nw.w;
+        for (int u = 0; u < UN; ++u) {
+            const int k = kb + u * PPI + pi;
+            fl[u] = 0; hcl[u] = 0; offR[u] = 0; offF[u] = 0;
+            if (k < ncov) {
+                const int ox = hx0 + k / ncy, oy = hy0 + k % ncy;
+                const int h = ox * rf.Hy + oy;
+                const int hc = CS::ld(hcs + h);
+                if (hc != CS::ld(hcsPrev + h)) {
+                    const int ylo = __ldg(rf.loy + oy);
+                    const int dx = vx - __ldg(rf.lox + ox);
+                    const int g8 = hc & ~7;
+                    // R row of hidden cell g8 (the group's first), this visible column; consecutive hidden cells: + PR * Z floats
+                    offR[u] = r_block(rf, ox, oy) +
+                              ((((long long)dx * __ldg(rf.ngr + oy) + (vy / PR - ylo / PR)) * rf.Hz + g8) * PR + (vy % PR)) * Z;
+                    const int qh = oy / rf.pf, ph = oy % rf.pf;
+                    // F: forward row of visible cell 0, hidden cell g8; consecutive visible cells: + fstep floats
+                    offF[u] = f_block(rf, ox, qh) +
+                              (((long long)dx * __ldg(rf.nyf + qh) + (vy - __ldg(rf.loyf + qh))) * Z * rf.pf + ph) * rf.Hz + g8;
+                    fl[u] = 1 | ((ox >= A.fx0 && ox < A.fx1) ? 2 : 0);
+                    hcl[u] = hc & 7;
                 }
             }
         }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+                if (fl[u]) w[u][j] = ld_plain(wrm + offR[u] + (long long)hz8[j] * (PR * Z) + q4[j]);
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+            if (fl[u]) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    float4 nw = w[u][j];
+                    if (hz8[j] == hcl[u]) {
+                        nw.x += delta[j].x; nw.y += delta[j].y; nw.z += delta[j].z; nw.w += delta[j].w;
+                        st_plain(wrm + offR[u] + (long long)hz8[j] * (PR * Z) + q4[j], nw);
+                        if (q4[j] == 0) nupd++;
+                    }
+                    if (fl[u] & 2) {
+                        float *f = wfm + offF[u] + (long long)q4[j] * fstep + hz8[j];
+                        f[0] = nw.x; f[fstep] = nw.y; f[2 * fstep] = nw.z; f[3 * fstep] = nw.w;
+                    }
+                }
+            }
+    }
     return nupd;
 }
 template <int Z> struct UpdV2 {
-    static constexpr int SL = 2 * Z, PPI = SL >= 32 ? 1 : 32 / SL, ITEMS = PPI * 4; // cover items per work unit
+    static constexpr int SL = 2 * Z, PPI = SL >= 32 ? 1 : 32 / SL, ITEMS = PPI * 4; // cover items per batch; a unit is `batches` of them
 };
 template <int Z> struct UpdV1 {
     static constexpr int ITEMS = (32 / (Z / 4)) * 4;
@@ -808,8 +812,8 @@ template <int Z, int VER>
 __global__ void __launch_bounds__(kThreads)
 k_sc_update_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ hcsAll, const int *__restrict__ hcsPrevAll,
               const int2 *__restrict__ work, unsigned *workCount, unsigned *doneCount, float alpha, unsigned long long *updCount,
-              int chunksPerEntry) {
-    constexpr int ITEMS = VER == 2 ? UpdV2<Z>::ITEMS : UpdV1<Z>::ITEMS;
+              int chunksPerEntry, int batches) {
+    const int ITEMS = VER == 2 ? UpdV2<Z>::ITEMS * batches : UpdV1<Z>::ITEMS;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
     const unsigned n = *(volatile unsigned *)workCount;
@@ -819,7 +823,7 @@ k_sc_update_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ 
         const unsigned e = (unsigned)(unit / (unsigned)chunksPerEntry);
         const int k0 = (int)(unit - (unsigned long long)e * (unsigned)chunksPerEntry) * ITEMS;
         const int2 wk = work[e];
-        if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, CsNc, false>(A, hcsAll, hcsPrevAll, wk, k0, alpha);
+        if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, CsNc, false>(A, hcsAll, hcsPrevAll, wk, k0, batches, alpha);
         else nupd += sc_update_unit_v1<Z, CsNc, false>(A, hcsAll, hcsPrevAll, wk, k0, alpha);
     }
     // bookkeeping: pairs rewritten, and the last warp out empties the list
@@ -889,7 +893,7 @@ __device__ __noinline__ void small_recon(const ogn_small_phase &P, int member, i
 }
 template <int Z, int VER>
 __device__ __noinline__ void small_update(const ogn_small_phase &P, int member, int nb, unsigned *cnt) {
-    constexpr int ITEMS = VER == 2 ? UpdV2<Z>::ITEMS : UpdV1<Z>::ITEMS;
+    const int ITEMS = VER == 2 ? UpdV2<Z>::ITEMS * P.updBatches : UpdV1<Z>::ITEMS;
     const int2 *work = reinterpret_cast<const int2 *>(P.work) + (long long)member * P.workStride;
     const unsigned n = __ldcg(cnt);
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = nb * (blockDim.x >> 5);
@@ -899,7 +903,7 @@ __device__ __noinline__ void small_update(const ogn_small_phase &P, int member, 
         const unsigned e = (unsigned)(unit / P.chunks);
         const int c = (int)(unit - (long long)e * P.chunks);
         const int2 wk = __ldcg(work + e);
-        if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, CsCg, true>(P.u.learn, P.hcs, P.hcsPrev, wk, c * ITEMS, P.alpha);
+        if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, CsCg, true>(P.u.learn, P.hcs, P.hcsPrev, wk, c * ITEMS, P.updBatches, P.alpha);
         else nupd += sc_update_unit_v1<Z, CsCg, true>(P.u.learn, P.hcs, P.hcsPrev, wk, c * ITEMS, P.alpha);
     }
 #pragma unroll
