@@ -99,6 +99,16 @@ typedef struct ogn_hierarchy_desc {
     int P##set_pred_alpha(void *h, int l, int p, float alpha);                                                     \
     int P##set_actor_params(void *h, int p, float alpha, float beta, float gamma, int min_steps,                   \
                             int history_iters);                                                                    \
+    /* ... and reading them back (`h.getSCLayer(l).alpha` in user code), plus the layer shapes: SparseCoder /      \
+       Predictor / Actor::getHiddenSize and getVisibleLayerDesc (SparseCoder.h:129-147, Predictor.h:128-146,       \
+       Actor.h:160-178). kind: 0 SparseCoder of layer l, 1 + p Predictor p of layer l, -1 - p Actor of input p     \
+       (l ignored). hidden_size writes 3 ints; visible_desc writes {size.x, size.y, size.z, radius}. */            \
+    float P##get_sc_alpha(void *h, int l);                                                                         \
+    float P##get_pred_alpha(void *h, int l, int p);                                                                \
+    int P##get_actor_params(void *h, int p, float *alpha, float *beta, float *gamma, int *min_steps,               \
+                            int *history_iters);                                                                   \
+    int P##layer_hidden_size(void *h, int kind, int l, int *out3);                                                 \
+    int P##layer_visible_desc(void *h, int kind, int l, int vli, int *out4);                                       \
     /* Hierarchy::writeToStream / readFromStream on a file, Hierarchy.cpp:287-432 (byte layout: SURVEY.md App. B). \
        save returns bytes written or -1. load creates a new handle whose ComputeSystem rng is seeded with seed. */ \
     int64_t P##save(void *h, const char *path);                                                                    \

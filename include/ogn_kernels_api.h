@@ -176,7 +176,7 @@ typedef struct ogn_small_phase {
         ogn_learn_args learn;
         ogn_pred_args pred;
     } u;
-} ogn_small_phase;
+} __attribute__((aligned(16))) ogn_small_phase; /* copied into shared memory with 16-byte loads */
 
 const char *ogn_cuda_error_string(int code);
 

@@ -1158,7 +1158,7 @@ int ogn_hier_small_max_blocks(int threads) {
     int dev = 0, sms = 0, per = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, vec::k_hier_step_small<32>, threads, 0) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, vec::k_hier_step_small<32, vec::CsCg>, threads, 48 * 1024) != cudaSuccess) return 0;
     return sms * per;
 }
 
@@ -1171,14 +1171,18 @@ int ogn_hier_step_small(const ogn_small_phase *phases, int nphases, const ogn_sm
     ogn_small_inputs in;
     memset(&in, 0, sizeof(in));
     if (inputs) in = *inputs;
-    if (blocks_per_member == 1) {
-        if (wide) vec::k_hier_step_small<32><<<grid, threads, 0, (cudaStream_t)stream>>>(phases, nphases, in, counters, cpm);
-        else vec::k_hier_step_small<8><<<grid, threads, 0, (cudaStream_t)stream>>>(phases, nphases, in, counters, cpm);
+    // the phase array goes to shared memory when it fits the default 48 KB (a 4-layer step is ~35 KB)
+    int phaseBytes = nphases * (int)sizeof(ogn_small_phase);
+    if (phaseBytes > 48 * 1024) phaseBytes = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (blocks_per_member == 1) { // one block owns a member: CSDRs written by the block are read back through its own L1
+        if (wide) vec::k_hier_step_small<32, vec::CsSm><<<grid, threads, phaseBytes, st>>>(phases, nphases, in, counters, cpm, phaseBytes);
+        else vec::k_hier_step_small<8, vec::CsSm><<<grid, threads, phaseBytes, st>>>(phases, nphases, in, counters, cpm, phaseBytes);
         return launch_status();
     }
-    void *kargs[] = {(void *)&phases, (void *)&nphases, (void *)&in, (void *)&counters, (void *)&cpm};
-    const void *fn = wide ? (const void *)vec::k_hier_step_small<32> : (const void *)vec::k_hier_step_small<8>;
-    return (int)cudaLaunchCooperativeKernel(fn, grid, dim3((unsigned)threads), kargs, 0, (cudaStream_t)stream);
+    void *kargs[] = {(void *)&phases, (void *)&nphases, (void *)&in, (void *)&counters, (void *)&cpm, (void *)&phaseBytes};
+    const void *fn = wide ? (const void *)vec::k_hier_step_small<32, vec::CsCg> : (const void *)vec::k_hier_step_small<8, vec::CsCg>;
+    return (int)cudaLaunchCooperativeKernel(fn, grid, dim3((unsigned)threads), kargs, (size_t)phaseBytes, st);
 }
 
 int ogn_actor_forward(const ogn_actor_args *args, int Hx, int Hy, int Hz, const float *u01, float *hidden_values,

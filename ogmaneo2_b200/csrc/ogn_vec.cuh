@@ -826,13 +826,15 @@ k_sc_update_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ 
         if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, CsNc, false>(A, hcsAll, hcsPrevAll, wk, k0, batches, alpha);
         else nupd += sc_update_unit_v1<Z, CsNc, false>(A, hcsAll, hcsPrevAll, wk, k0, alpha);
     }
-    // bookkeeping: pairs rewritten, and the last warp out empties the list
+    // bookkeeping: pairs rewritten, and the last BLOCK out empties the list (one atomic per block: a launch with little work
+    // used to spend most of its time on 9472 warps queueing at one L2 atomic)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nupd += __shfl_xor_sync(0xffffffffu, nupd, o);
-    if (lane == 0) {
-        if (updCount && nupd) atomicAdd(updCount, (unsigned long long)nupd);
+    if (lane == 0 && updCount && nupd) atomicAdd(updCount, (unsigned long long)nupd);
+    __syncthreads(); // every warp of the block has read the list for the last time
+    if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(doneCount, 1u) == (unsigned)nwarps - 1u) { *workCount = 0; *doneCount = 0; __threadfence(); }
+        if (atomicAdd(doneCount, 1u) == gridDim.x - 1u) { *workCount = 0; *doneCount = 0; __threadfence(); }
     }
 }
 
@@ -876,22 +878,22 @@ __device__ __forceinline__ void member_barrier(unsigned *bar, int nb) {
 
 // One phase body per (kind, row width, mapping), compiled as separate functions (noinline) so that each keeps the register
 // allocation of its stand-alone kernel instead of the union of all of them.
-template <int Z, int W>
+template <int Z, int W, class CS>
 __device__ __noinline__ void small_fwd(const ogn_small_phase &P, int member, int unit0, int stride) {
     for (int pack = unit0; pack < P.npacks; pack += stride)
-        sc_forward_pack<Z, 1, W, CsCg>(P.u.fwd, P.Hx, P.Hy, 0, pack, P.ppr, member, P.out0, P.out1, nullptr);
+        sc_forward_pack<Z, 1, W, CS>(P.u.fwd, P.Hx, P.Hy, 0, pack, P.ppr, member, P.out0, P.out1, nullptr);
 }
-template <int Z, int W>
+template <int Z, int W, class CS>
 __device__ __noinline__ void small_recon(const ogn_small_phase &P, int member, int unit0, int stride, unsigned *cnt) {
     int2 *work = reinterpret_cast<int2 *>(P.work) + (long long)member * P.workStride;
     const int total = P.npacks * P.u.learn.nvl; // (visible layer, pack) pairs
     for (int it = unit0; it < total; it += stride) {
         const int vli = it / P.npacks, pack = it - vli * P.npacks;
         // the tag keeps the stand-alone encoding member * nvl + vli so that the update units decode it the same way
-        sc_recon_pack<Z, 1, W, CsCg>(P.u.learn, vli, P.hcs, 0, pack, P.ppr, member, member * P.u.learn.nvl + vli, work, cnt);
+        sc_recon_pack<Z, 1, W, CS>(P.u.learn, vli, P.hcs, 0, pack, P.ppr, member, member * P.u.learn.nvl + vli, work, cnt);
     }
 }
-template <int Z, int VER>
+template <int Z, int VER, class CS>
 __device__ __noinline__ void small_update(const ogn_small_phase &P, int member, int nb, unsigned *cnt) {
     const int ITEMS = VER == 2 ? UpdV2<Z>::ITEMS * P.updBatches : UpdV1<Z>::ITEMS;
     const int2 *work = reinterpret_cast<const int2 *>(P.work) + (long long)member * P.workStride;
@@ -903,17 +905,17 @@ __device__ __noinline__ void small_update(const ogn_small_phase &P, int member, 
         const unsigned e = (unsigned)(unit / P.chunks);
         const int c = (int)(unit - (long long)e * P.chunks);
         const int2 wk = __ldcg(work + e);
-        if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, CsCg, true>(P.u.learn, P.hcs, P.hcsPrev, wk, c * ITEMS, P.updBatches, P.alpha);
-        else nupd += sc_update_unit_v1<Z, CsCg, true>(P.u.learn, P.hcs, P.hcsPrev, wk, c * ITEMS, P.alpha);
+        if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, CS, true>(P.u.learn, P.hcs, P.hcsPrev, wk, c * ITEMS, P.updBatches, P.alpha);
+        else nupd += sc_update_unit_v1<Z, CS, true>(P.u.learn, P.hcs, P.hcsPrev, wk, c * ITEMS, P.alpha);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nupd += __shfl_xor_sync(0xffffffffu, nupd, o);
     if ((threadIdx.x & 31) == 0 && P.updCount && nupd) atomicAdd(P.updCount, (unsigned long long)nupd);
 }
-template <int Z, int W>
+template <int Z, int W, class CS>
 __device__ __noinline__ void small_pred(const ogn_small_phase &P, int member, int unit0, int stride) {
     for (int pack = unit0; pack < P.npacks; pack += stride)
-        pred_step_pack<Z, 1, W, CsCg>(P.u.pred, P.Hx, P.Hy, 0, pack, P.ppr, member, P.learn, P.activate, P.target, P.alpha, P.acts, P.out0,
+        pred_step_pack<Z, 1, W, CS>(P.u.pred, P.Hx, P.Hy, 0, pack, P.ppr, member, P.learn, P.activate, P.target, P.alpha, P.acts, P.out0,
                                       nullptr);
 }
 
@@ -925,20 +927,29 @@ __device__ __noinline__ void small_pred(const ogn_small_phase &P, int member, in
     }
 
 // counters: per member OGN_SMALL_COUNTERS words: [0..1] barrier {arrivals, generation}, [2 + i] fill of work list i. All are
-// zero between launches. W = lanes per pack of every phase of the launch (8: ensembles, 32: a single small hierarchy).
-template <int W>
+// zero between launches. W = lanes per pack of every phase of the launch (8: ensembles, 32: a single small hierarchy). CS =
+// how CSDRs produced earlier in the launch are read: plain cached loads when ONE block owns the member (an SM's L1 is
+// coherent with its own stores), L2 loads (CsCg) when several blocks share it. phaseBytes > 0: the phase array is first
+// copied into dynamic shared memory, so that every descriptor read of the phase loop is an LDS instead of an L2 access.
+template <int W, class CS>
 __global__ void __launch_bounds__(512, 1)
 k_hier_step_small(const ogn_small_phase *__restrict__ phases, int nphases, const __grid_constant__ ogn_small_inputs I, unsigned *counters,
-                  int countersPerMember) {
+                  int countersPerMember, int phaseBytes) {
     const int member = blockIdx.y, nb = gridDim.x;
     unsigned *mc = counters + (long long)member * countersPerMember;
+    if (phaseBytes > 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(phases);
+        uint4 *dst = reinterpret_cast<uint4 *>(ogn_dyn_smem);
+        for (int i = threadIdx.x; i < phaseBytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+        phases = reinterpret_cast<const ogn_small_phase *>(ogn_dyn_smem);
+    }
     if (I.n > 0) { // K1: every block copies its member's inputs itself (identical values), so no block waits for another
         for (int i = 0; i < I.n; ++i) {
             const long long mo = (long long)member * I.count[i];
             for (int k = threadIdx.x; k < I.count[i]; k += blockDim.x) I.dst[i][mo + k] = __ldg(I.src[i] + mo + k);
         }
-        __syncthreads();
     }
+    __syncthreads();
     // units of this block: octets (W = 8) or warps (W = 32), strided over the member's blocks
     const int unitsPerBlock = blockDim.x / W, unit0 = blockIdx.x * unitsPerBlock + threadIdx.x / W, stride = nb * unitsPerBlock;
     for (int ph = 0; ph < nphases; ++ph) {
@@ -946,26 +957,26 @@ k_hier_step_small(const ogn_small_phase *__restrict__ phases, int nphases, const
         unsigned *cnt = mc + 2 + P.counter;
         switch (P.kind) {
         case OGN_PHASE_SC_FORWARD:
-            OGN_SMALL_Z((small_fwd<8, W>(P, member, unit0, stride)), (small_fwd<16, W>(P, member, unit0, stride)),
-                        (small_fwd<32, W>(P, member, unit0, stride)));
+            OGN_SMALL_Z((small_fwd<8, W, CS>(P, member, unit0, stride)), (small_fwd<16, W, CS>(P, member, unit0, stride)),
+                        (small_fwd<32, W, CS>(P, member, unit0, stride)));
             break;
         case OGN_PHASE_SC_RECON:
-            OGN_SMALL_Z((small_recon<8, W>(P, member, unit0, stride, cnt)), (small_recon<16, W>(P, member, unit0, stride, cnt)),
-                        (small_recon<32, W>(P, member, unit0, stride, cnt)));
+            OGN_SMALL_Z((small_recon<8, W, CS>(P, member, unit0, stride, cnt)), (small_recon<16, W, CS>(P, member, unit0, stride, cnt)),
+                        (small_recon<32, W, CS>(P, member, unit0, stride, cnt)));
             break;
         case OGN_PHASE_SC_UPDATE:
             if (P.updVer == 2) {
-                OGN_SMALL_Z((small_update<8, 2>(P, member, nb, cnt)), (small_update<16, 2>(P, member, nb, cnt)),
-                            (small_update<32, 2>(P, member, nb, cnt)));
+                OGN_SMALL_Z((small_update<8, 2, CS>(P, member, nb, cnt)), (small_update<16, 2, CS>(P, member, nb, cnt)),
+                            (small_update<32, 2, CS>(P, member, nb, cnt)));
             } else {
-                OGN_SMALL_Z((small_update<8, 1>(P, member, nb, cnt)), (small_update<16, 1>(P, member, nb, cnt)),
-                            (small_update<32, 1>(P, member, nb, cnt)));
+                OGN_SMALL_Z((small_update<8, 1, CS>(P, member, nb, cnt)), (small_update<16, 1, CS>(P, member, nb, cnt)),
+                            (small_update<32, 1, CS>(P, member, nb, cnt)));
             }
             break;
         case OGN_PHASE_PRED:
-            if (P.activate == 1) pred_copy_inputs<CsCg>(P.u.pred, member, blockIdx.x * blockDim.x + threadIdx.x, nb * blockDim.x);
-            OGN_SMALL_Z((small_pred<8, W>(P, member, unit0, stride)), (small_pred<16, W>(P, member, unit0, stride)),
-                        (small_pred<32, W>(P, member, unit0, stride)));
+            if (P.activate == 1) pred_copy_inputs<CS>(P.u.pred, member, blockIdx.x * blockDim.x + threadIdx.x, nb * blockDim.x);
+            OGN_SMALL_Z((small_pred<8, W, CS>(P, member, unit0, stride)), (small_pred<16, W, CS>(P, member, unit0, stride)),
+                        (small_pred<32, W, CS>(P, member, unit0, stride)));
             break;
         default: break;
         }

@@ -81,6 +81,11 @@ _SIGS = {
     "set_sc_alpha": (C.c_int, [_VP, C.c_int, C.c_float]),
     "set_pred_alpha": (C.c_int, [_VP, C.c_int, C.c_int, C.c_float]),
     "set_actor_params": (C.c_int, [_VP, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]),
+    "get_sc_alpha": (C.c_float, [_VP, C.c_int]),
+    "get_pred_alpha": (C.c_float, [_VP, C.c_int, C.c_int]),
+    "get_actor_params": (C.c_int, [_VP, C.c_int, _FP, _FP, _FP, _IP, _IP]),
+    "layer_hidden_size": (C.c_int, [_VP, C.c_int, C.c_int, _IP]),
+    "layer_visible_desc": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _IP]),
     "save": (C.c_int64, [_VP, C.c_char_p]),
     "load": (C.c_int, [C.c_char_p, C.c_uint32, C.POINTER(_VP)]),
     "get_state": (C.c_int, [_VP, C.POINTER(_VP)]),
@@ -240,6 +245,27 @@ class FlatHierarchy:
 
     def setActorParams(self, p, alpha=0.02, beta=0.02, gamma=0.99, minSteps=8, historyIters=8):
         self._chk(self.f.set_actor_params(self.h, p, alpha, beta, gamma, minSteps, historyIters), "set_actor_params")
+
+    def getSCAlpha(self, l): return float(self.f.get_sc_alpha(self.h, l))
+    def getPredAlpha(self, l, p): return float(self.f.get_pred_alpha(self.h, l, p))
+
+    def getActorParams(self, p) -> dict:
+        a, b, g = C.c_float(), C.c_float(), C.c_float()
+        ms, hi = C.c_int(), C.c_int()
+        self._chk(self.f.get_actor_params(self.h, p, C.byref(a), C.byref(b), C.byref(g), C.byref(ms), C.byref(hi)), "get_actor_params")
+        return dict(alpha=a.value, beta=b.value, gamma=g.value, minSteps=ms.value, historyIters=hi.value)
+
+    def layerHiddenSize(self, kind: int, l: int = 0) -> tuple:
+        """kind: 0 SparseCoder of layer l, 1 + p Predictor p of layer l, -1 - p Actor of input p."""
+        out = (C.c_int * 3)()
+        self._chk(self.f.layer_hidden_size(self.h, kind, l, out), "layer_hidden_size")
+        return tuple(out)
+
+    def layerVisibleDesc(self, kind: int, l: int, vli: int) -> tuple:
+        """(size.x, size.y, size.z, radius) of visible layer vli; kind as in layerHiddenSize."""
+        out = (C.c_int * 4)()
+        self._chk(self.f.layer_visible_desc(self.h, kind, l, vli, out), "layer_visible_desc")
+        return tuple(out)
 
     def save(self, path: str) -> int:
         n = self.f.save(self.h, path.encode())

@@ -75,6 +75,106 @@ class LayerDesc:
                               historyCapacity=self.historyCapacity)
 
 
+class _SCLayer:
+    """What `h.getSCLayer(l)` hands out: ogmaneo::SparseCoder's public members and getters (SparseCoder.h:83-147) as live
+    properties of the device-resident layer (reads and writes go through the flat ABI)."""
+
+    def __init__(self, h, l):
+        self._h, self._l = h, l
+
+    @property
+    def alpha(self) -> float:
+        return self._h.getSCAlpha(self._l)
+
+    @alpha.setter
+    def alpha(self, v: float):
+        self._h.setSCAlpha(self._l, float(v))
+
+    def getHiddenCs(self) -> List[int]: return self._h.scHiddenCs(self._l).tolist()
+    def getHiddenCsPrev(self) -> List[int]: return self._h.scHiddenCsPrev(self._l).tolist()
+    def getHiddenSize(self) -> Int3: return Int3(*self._h.layerHiddenSize(0, self._l))
+    def getNumVisibleLayers(self) -> int: return self._h.scNumVisible(self._l)
+
+    def getVisibleLayerDesc(self, v: int) -> "VisibleLayerDesc":
+        d = self._h.layerVisibleDesc(0, self._l, v)
+        return VisibleLayerDesc(Int3(*d[:3]), d[3])
+
+    def getWeights(self, v: int) -> np.ndarray:
+        """getVisibleLayer(v).weights.nonZeroValues (reference CSR order)."""
+        return self._h.scWeights(self._l, v)
+
+
+class _PLayer:
+    """An element of `h.getPLayers(l)`: ogmaneo::Predictor (Predictor.h:82-146)."""
+
+    def __init__(self, h, l, p):
+        self._h, self._l, self._p = h, l, p
+
+    @property
+    def alpha(self) -> float:
+        return self._h.getPredAlpha(self._l, self._p)
+
+    @alpha.setter
+    def alpha(self, v: float):
+        self._h.setPredAlpha(self._l, self._p, float(v))
+
+    def getHiddenCs(self) -> List[int]: return self._h.predHiddenCs(self._l, self._p).tolist()
+    def getHiddenSize(self) -> Int3: return Int3(*self._h.layerHiddenSize(1 + self._p, self._l))
+    def getNumVisibleLayers(self) -> int: return self._h.predNumVisible(self._l, self._p)
+
+    def getVisibleLayerDesc(self, v: int) -> "VisibleLayerDesc":
+        d = self._h.layerVisibleDesc(1 + self._p, self._l, v)
+        return VisibleLayerDesc(Int3(*d[:3]), d[3])
+
+    def getWeights(self, v: int) -> np.ndarray: return self._h.predWeights(self._l, self._p, v)
+
+
+class _ALayer:
+    """An element of `h.getALayers()`: ogmaneo::Actor (Actor.h:108-179); alpha, beta, gamma, minSteps and historyIters
+    are live properties."""
+
+    def __init__(self, h, p):
+        object.__setattr__(self, "_h", h)
+        object.__setattr__(self, "_p", p)
+
+    _PARAMS = ("alpha", "beta", "gamma", "minSteps", "historyIters")
+
+    def __getattr__(self, name):
+        if name in _ALayer._PARAMS:
+            return self._h.getActorParams(self._p)[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name not in _ALayer._PARAMS:
+            raise AttributeError(name)
+        cur = self._h.getActorParams(self._p)
+        cur[name] = value
+        self._h.setActorParams(self._p, float(cur["alpha"]), float(cur["beta"]), float(cur["gamma"]), int(cur["minSteps"]),
+                               int(cur["historyIters"]))
+
+    def getHiddenCs(self) -> List[int]: return self._h.actorHiddenCs(self._p).tolist()
+    def getHiddenSize(self) -> Int3: return Int3(*self._h.layerHiddenSize(-1 - self._p))
+    def getNumVisibleLayers(self) -> int: return self._h.actorNumVisible(self._p)
+
+    def getVisibleLayerDesc(self, v: int) -> "VisibleLayerDesc":
+        d = self._h.layerVisibleDesc(-1 - self._p, 0, v)
+        return VisibleLayerDesc(Int3(*d[:3]), d[3])
+
+
+@dataclasses.dataclass
+class VisibleLayerDesc:
+    """SparseCoder / Predictor / Actor::VisibleLayerDesc (SparseCoder.h:18-29)."""
+    size: Int3
+    radius: int
+
+
+class State:
+    """ogmaneo::State (Hierarchy.h:26-36): what getState() returns and setState() takes."""
+
+    def __init__(self, opaque):
+        self._s = opaque
+
+
 class Hierarchy:
     """ogmaneo::Hierarchy (Hierarchy.h:90-215). Construct with (cs, inputSizes, inputTypes, layerDescs) — initRandom — or
     with (cs, fileName, inputSizes=...) — readFromStream."""
@@ -120,3 +220,40 @@ class Hierarchy:
     def save(self, fileName: str) -> int:
         """Hierarchy::writeToStream into a file (same bytes as the reference writes)."""
         return self._h.save(fileName)
+
+    # --- layers (Hierarchy.h:180-215): proxies whose attributes read and write the device-resident layer -----------------
+    def getSCLayer(self, l: int) -> _SCLayer:
+        return _SCLayer(self._h, l)
+
+    def getPLayers(self, l: int) -> list:
+        """One entry per predictor slot of layer l, None where the reference holds a null pointer."""
+        return [_PLayer(self._h, l, p) if self._h.predExists(l, p) else None for p in range(self._h.predCount(l))]
+
+    def getALayers(self) -> list:
+        return [_ALayer(self._h, p) if self._h.actorExists(p) else None for p in range(len(self._sizes))]
+
+    def getState(self) -> State:
+        return State(self._h.getState())
+
+    def setState(self, state: State):
+        self._h.setState(state._s)
+
+    # --- the flat accessors of the SWIG binding, for scripts that use those ----------------------------------------------
+    def getHiddenSize(self, l: int) -> Int3: return self.getSCLayer(l).getHiddenSize()
+    def getNumSCVisibleLayers(self, l: int) -> int: return self._h.scNumVisible(l)
+    def pLayerExists(self, l: int, v: int) -> bool: return self._h.predExists(l, v)
+    def aLayerExists(self, v: int) -> bool: return self._h.actorExists(v)
+    def getSCAlpha(self, l: int) -> float: return self._h.getSCAlpha(l)
+    def setSCAlpha(self, l: int, alpha: float): self._h.setSCAlpha(l, float(alpha))
+    def getPAlpha(self, l: int, v: int) -> float: return self._h.getPredAlpha(l, v)
+    def setPAlpha(self, l: int, v: int, alpha: float): self._h.setPredAlpha(l, v, float(alpha))
+    def getAAlpha(self, v: int) -> float: return self._h.getActorParams(v)["alpha"]
+    def setAAlpha(self, v: int, x: float): self.getALayers()[v].alpha = x
+    def getABeta(self, v: int) -> float: return self._h.getActorParams(v)["beta"]
+    def setABeta(self, v: int, x: float): self.getALayers()[v].beta = x
+    def getAGamma(self, v: int) -> float: return self._h.getActorParams(v)["gamma"]
+    def setAGamma(self, v: int, x: float): self.getALayers()[v].gamma = x
+    def getAMinSteps(self, v: int) -> int: return self._h.getActorParams(v)["minSteps"]
+    def setAMinSteps(self, v: int, x: int): self.getALayers()[v].minSteps = x
+    def getAHistoryIters(self, v: int) -> int: return self._h.getActorParams(v)["historyIters"]
+    def setAHistoryIters(self, v: int, x: int): self.getALayers()[v].historyIters = x

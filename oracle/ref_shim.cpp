@@ -146,6 +146,38 @@ int oref_set_actor_params(void *h, int p, float alpha, float beta, float gamma, 
     a.alpha = alpha; a.beta = beta; a.gamma = gamma; a.minSteps = minSteps; a.historyIters = historyIters;
     return 0;
 }
+float oref_get_sc_alpha(void *h, int l) { return ((Handle *)h)->h.getSCLayer(l).alpha; }
+float oref_get_pred_alpha(void *h, int l, int p) { return ((Handle *)h)->h.getPLayers(l)[p]->alpha; }
+int oref_get_actor_params(void *h, int p, float *alpha, float *beta, float *gamma, int *minSteps, int *historyIters) {
+    const Actor &a = *((Handle *)h)->h.getALayers()[p];
+    *alpha = a.alpha; *beta = a.beta; *gamma = a.gamma; *minSteps = a.minSteps; *historyIters = a.historyIters;
+    return 0;
+}
+} // extern "C"
+namespace {
+template <typename L> void shapeOut(const L &layer, int vli, int *out3, int *out4) {
+    if (out3) { const Int3 &s = layer.getHiddenSize(); out3[0] = s.x; out3[1] = s.y; out3[2] = s.z; }
+    if (out4) {
+        const auto &d = layer.getVisibleLayerDesc(vli);
+        out4[0] = d.size.x; out4[1] = d.size.y; out4[2] = d.size.z; out4[3] = d.radius;
+    }
+}
+int layerShape(void *hh, int kind, int l, int vli, int *out3, int *out4) {
+    Hierarchy &h = ((Handle *)hh)->h;
+    if (kind == 0) shapeOut(h.getSCLayer(l), vli, out3, out4);
+    else if (kind > 0) {
+        if (kind - 1 >= (int)h.getPLayers(l).size() || !h.getPLayers(l)[kind - 1]) return fail("no such predictor");
+        shapeOut(*h.getPLayers(l)[kind - 1], vli, out3, out4);
+    } else {
+        if (-1 - kind >= (int)h.getALayers().size() || !h.getALayers()[-1 - kind]) return fail("no such actor");
+        shapeOut(*h.getALayers()[-1 - kind], vli, out3, out4);
+    }
+    return 0;
+}
+} // namespace
+extern "C" {
+int oref_layer_hidden_size(void *h, int kind, int l, int *out3) { return layerShape(h, kind, l, 0, out3, nullptr); }
+int oref_layer_visible_desc(void *h, int kind, int l, int vli, int *out4) { return layerShape(h, kind, l, vli, nullptr, out4); }
 int64_t oref_save(void *h, const char *path) {
     std::ofstream os(path, std::ios::binary);
     if (!os) return -1;

@@ -771,6 +771,35 @@ int oport_set_actor_params(void *h, int p, float alpha, float beta, float gamma,
     a.alpha = alpha; a.beta = beta; a.gamma = gamma; a.minSteps = minSteps; a.historyIters = historyIters;
     return 0;
 }
+float oport_get_sc_alpha(void *h, int l) { return ((Hierarchy *)h)->sc[l].alpha; }
+float oport_get_pred_alpha(void *h, int l, int p) { return ((Hierarchy *)h)->p[l][p]->alpha; }
+int oport_get_actor_params(void *h, int p, float *alpha, float *beta, float *gamma, int *minSteps, int *historyIters) {
+    const Actor &a = *((Hierarchy *)h)->a[p];
+    *alpha = a.alpha; *beta = a.beta; *gamma = a.gamma; *minSteps = a.minSteps; *historyIters = a.historyIters;
+    return 0;
+}
+} // extern "C"
+template <typename L> static int portShape(const L &layer, int vli, int *out3, int *out4) {
+    if (out3) { out3[0] = layer.Hx; out3[1] = layer.Hy; out3[2] = layer.Hz; }
+    if (out4) {
+        if (vli < 0 || vli >= (int)layer.vlds.size()) { g_err = "no such visible layer"; return 1; }
+        out4[0] = layer.vlds[vli].x; out4[1] = layer.vlds[vli].y; out4[2] = layer.vlds[vli].z; out4[3] = layer.vlds[vli].radius;
+    }
+    return 0;
+}
+static int portLayerShape(void *hh, int kind, int l, int vli, int *out3, int *out4) {
+    Hierarchy &h = *(Hierarchy *)hh;
+    if (kind == 0) return portShape(h.sc[l], vli, out3, out4);
+    if (kind > 0) {
+        if (kind - 1 >= (int)h.p[l].size() || !h.p[l][kind - 1]) { g_err = "no such predictor"; return 1; }
+        return portShape(*h.p[l][kind - 1], vli, out3, out4);
+    }
+    if (-1 - kind >= (int)h.a.size() || !h.a[-1 - kind]) { g_err = "no such actor"; return 1; }
+    return portShape(*h.a[-1 - kind], vli, out3, out4);
+}
+extern "C" {
+int oport_layer_hidden_size(void *h, int kind, int l, int *out3) { return portLayerShape(h, kind, l, 0, out3, nullptr); }
+int oport_layer_visible_desc(void *h, int kind, int l, int vli, int *out4) { return portLayerShape(h, kind, l, vli, nullptr, out4); }
 int64_t oport_save(void *h, const char *path) { return saveHierarchy(*(Hierarchy *)h, path); }
 int oport_load(const char *path, uint32_t seed, void **out) {
     auto *h = new Hierarchy();

@@ -393,3 +393,42 @@ def test_pipelined_prediction_readback(product):
     rows = np.empty(30, np.int32)
     tk = b.predictionReadbackQueue(0, 2, 5)
     assert b.predictionReadbackFinish(tk, rows) == 30 and np.array_equal(rows, want[-1].reshape(10, 10)[2:5].reshape(-1))
+
+
+def test_pyogmaneo_layer_proxies(product, oracle):
+    """`h.getSCLayer(l).alpha = x`, Predictor / Actor parameters through the pyogmaneo-style proxies, getState / setState:
+    the values land in the device-resident layers (same trajectory as the checker given the same parameters)."""
+    from ogmaneo2_b200 import pyogmaneo as po
+    from common import reward_at
+    flat, kind = oracle
+    flat.set_num_threads(1)
+    cfg = configs.c3_actor(8)
+    cs = po.ComputeSystem(seed=cfg["seed"])
+    lds = []
+    for _ in range(3):
+        ld = po.LayerDesc()
+        ld.hiddenSize = po.Int3(8, 8, 16)
+        lds.append(ld)
+    h = po.Hierarchy(cs, [po.Int3(8, 8, 16), po.Int3(2, 2, 4)], [po.inputTypeNone, po.inputTypeAction], lds)
+    chk = FlatHierarchy(flat, cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], cfg["seed"])
+    h.getSCLayer(1).alpha = 0.25
+    h.getPLayers(1)[0].alpha = 0.125
+    act = h.getALayers()[1]
+    act.alpha, act.beta, act.minSteps, act.historyIters = 0.03, 0.015, 5, 6
+    chk.setSCAlpha(1, 0.25); chk.setPredAlpha(1, 0, 0.125); chk.setActorParams(1, 0.03, 0.015, 0.99, 5, 6)
+    assert abs(h.getSCLayer(1).alpha - 0.25) < 1e-7 and abs(act.gamma - 0.99) < 1e-6 and act.historyIters == 6
+    assert h.getALayers()[0] is None and h.getPLayers(0) == [None, None]
+    assert tuple(h.getSCLayer(0).getHiddenSize()) == (8, 8, 16) and h.getSCLayer(0).getVisibleLayerDesc(0).radius == 2
+    assert tuple(act.getHiddenSize()) == (2, 2, 4)
+    action = [0, 0, 0, 0]
+    for t in range(40):
+        ins = make_inputs(cfg, t, np.asarray(action, dtype=np.int32))
+        h.step(cs, [ins[0].tolist(), action], True, reward_at(t))
+        chk.step(ins, True, reward_at(t))
+        action = h.getPredictionCs(1)
+        assert action == chk.getPredictionCs(1).tolist(), f"[checker={kind}] action differs at step {t}"
+    st = h.getState()
+    first = h.getSCLayer(0).getHiddenCs()
+    h.step(cs, [make_inputs(cfg, 40)[0].tolist(), action], False)
+    h.setState(st)
+    assert h.getSCLayer(0).getHiddenCs() == first

@@ -205,3 +205,30 @@ def test_port_get_set_state_like_the_reference():
         pytest.skip("oracle/_ref not built (no reference sources on this box)")
     ref.set_num_threads(1)
     state_rewind_check(maker(loader.port()), maker(ref), configs.c2_video(8, 3), "port vs reference")
+
+
+def test_port_layer_getters_like_the_reference():
+    """The shape / hyper-parameter getters of the flat ABI (layer_hidden_size, layer_visible_desc, get_*_alpha,
+    get_actor_params) answer the same on the port and on the compiled reference, before and after setters."""
+    ref = loader.ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no reference sources on this box)")
+    cfg = configs.c3_actor(8)
+    a, b = maker(loader.port())(cfg), maker(ref)(cfg)
+    for h in (a, b):
+        h.setSCAlpha(1, 0.25)
+        h.setPredAlpha(1, 0, 0.125)
+        h.setActorParams(1, 0.03, 0.015, 0.97, 5, 6)
+    def facts(h):
+        out = []
+        for l in range(h.getNumLayers()):
+            out.append((h.getSCAlpha(l), h.layerHiddenSize(0, l), [h.layerVisibleDesc(0, l, v) for v in range(h.scNumVisible(l))]))
+            for p in range(h.predCount(l)):
+                if h.predExists(l, p):
+                    out.append((h.getPredAlpha(l, p), h.layerHiddenSize(1 + p, l),
+                                [h.layerVisibleDesc(1 + p, l, v) for v in range(h.predNumVisible(l, p))]))
+        out.append((sorted(h.getActorParams(1).items()), h.layerHiddenSize(-2), [h.layerVisibleDesc(-2, 0, v) for v in range(h.actorNumVisible(1))]))
+        return out
+    fa, fb = facts(a), facts(b)
+    assert fa == fb
+    assert fa[1][0] == 0.25 and dict(fa[-1][0])["historyIters"] == 6 and fa[-1][1] == (2, 2, 4)
