@@ -85,7 +85,7 @@ struct DeviceContext {
     bool graphs = true, dry = false, dryUncounted = false;
     // non-null: layers append the phases they would launch to this plan (and launch nothing), see SmallPlan
     SmallPlan *collect = nullptr;
-    bool small = true;      // OGN_SMALL_KERNEL=0 disables the single-launch path for small hierarchies
+    bool small = false;     // OGN_SMALL_KERNEL=1: small hierarchies step through the single-launch kernel (ogn_hier_step_small)
     int smallMaxUnits = 8192;
     void forkSide();
     void learnQueued();     // call after queueing learn work on `side`

@@ -997,9 +997,10 @@ int ogn_sc_update_version(const ogn_learn_args *args) {
     static int forced = -1;
     if (forced < 0) forced = env_int("OGN_SC_UPDATE", 0);
     const bool v2ok = args->geo.Hz % 8 == 0;
-    if (forced == 1) return 1;
+    // default: version 1. Version 2 (full 32-byte sector stores into F) was measured on B200 (profiles/README.md): the L2
+    // still fills the sector from DRAM (the DRAM-side write atom is 64 bytes), so it only adds the R group reads.
     if (forced == 2) return v2ok ? 2 : 1;
-    return v2ok ? 2 : 1;
+    return 1;
 }
 int ogn_sc_update_batches(void) {
     static int b = -1;
