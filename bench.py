@@ -45,15 +45,15 @@ UNIT = "steps/s"
 def load_traffic():
     """kernel kind -> DRAM bytes per launch at the default workload, read from the committed summary of the latest
     `ncu --set full` capture (profiles/ncu_c4_512_traffic.csv: kind,kernel,dram_bytes_read,dram_bytes_write,source)."""
-    out, src = {}, None
+    out, src = {}, {}
     try:
         with open(TRAFFIC_CSV) as f:
             for line in f:
                 p = [x.strip() for x in line.split(",")]
                 if len(p) >= 5 and p[0] != "kind" and not p[0].startswith("#"):
                     out[p[0]] = float(p[2]) + float(p[3])
-                    src = p[4]
-    except OSError:
+                    src[p[0]] = p[4]
+    except (OSError, ValueError):
         pass
     return out, src
 
@@ -639,8 +639,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["achieved_gbs"] / peak if dom else None,
                 "traffic": traffic.get(dom) if args.workload == "c4" and world == 1 and not args.size else None,
-                "traffic_source": (f"profiles/ncu_c4_512_traffic.csv <- {traffic_src} (ncu --set full, dram__bytes_read.sum + "
-                                   "dram__bytes_write.sum per launch)") if traffic else None,
+                "traffic_source": (f"profiles/ncu_c4_512_traffic.csv <- {traffic_src.get(dom)} (ncu --set full, dram__bytes_read.sum + "
+                                   "dram__bytes_write.sum per launch)") if traffic.get(dom) else None,
                 "peak_source": peak_src,
                 "step_achieved_gbs": total_alg / (ms * 1e-3) / 1e9, "step_frac": total_alg / (ms * 1e-3) / 1e9 / peak,
                 "alg_bytes_per_step_per_gpu": total_alg / K, "kernels": kernels,
