@@ -249,6 +249,30 @@ int ogn_actor_forward(const ogn_actor_args *args_host, int Hx, int Hy, int Hz, c
 int ogn_actor_learn(const ogn_actor_args *args_host, const ogn_actor_batch *batch_host, int Hx, int Hy, int Hz,
                     const float *hidden_values, float alpha, float beta, int mimic, float *hidden_activations, void *stream);
 
+/* ImageEncoder (ImageEncoder.cpp:19-94): dense fp32 inputs, weights in the F layout (every visible cell of
+ * every slot is read, so a column pack streams its block front to back). */
+#define OGN_MAX_IENC_VL 8
+typedef struct ogn_ienc_vl {
+    float *wf;                    /* F layout virtual base */
+    const float *in;              /* dense input [Vx][Vy][Vz] (address3, Helpers.h:247-252) */
+    float *recon;                 /* reconstructions [Vx][Vy][Vz] */
+    int geo, pad;
+} ogn_ienc_vl;
+typedef struct ogn_ienc_args {
+    ogn_rf geo[OGN_MAX_GEO];
+    ogn_ienc_vl vl[OGN_MAX_IENC_VL];
+    int nvl;
+} ogn_ienc_args;
+/* ImageEncoder::forward for every hidden column (ImageEncoder.cpp:19-74): activation = -sum of squared distances
+ * (SparseMatrix::distance2 :122-137), first-max arg-max -> hidden_cs; with learn != 0 the cells of a column are ranked by
+ * activation (descending, stable), strength = expf(-rank^2 * gamma / max(0.001, resource)) * resource, resource -= alpha *
+ * strength, and every weight of the cell moves towards its input by strength (SparseMatrix::hebb :692-701). Hz <= 32. */
+int ogn_image_encoder_step(const ogn_ienc_args *args_host, int Hx, int Hy, int Hz, int learn, float alpha, float gamma, float *resources,
+                  int *hidden_cs, void *stream);
+/* ImageEncoder::backward for every cell of visible layer vli (ImageEncoder.cpp:76-94): the weights of the active cells of the
+ * covering hidden columns, summed in ascending column order, divided by max(1, number of covering columns). */
+int ogn_image_encoder_reconstruct(const ogn_ienc_args *args_host, int vli, int Hx, int Hy, int Hz, const int *hidden_cs, void *stream);
+
 /* Peer-memory all-gather of a sharded CSDR (multi-GPU, one process per GPU): base[r] is rank r's exchange arena as mapped
  * in THIS process (CUDA IPC); the buffer lives at the same offset in every arena. One launch: this rank's slab
  * [rank*count, (rank+1)*count) is stored into every peer's arena with 128-bit NVLink stores, the last block to finish

@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-prec-sqrt=true", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", CXX]
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-Wall", "-Wno-sign-compare", f"-I{CUDA}/include",
              f"-I{ROOT}/include"]
-HOST_SOURCES = ["Device", "Helpers", "SparseCoder", "Predictor", "Actor", "Hierarchy", "FlatApi"]
+HOST_SOURCES = ["Device", "Helpers", "SparseCoder", "Predictor", "Actor", "Hierarchy", "ImageEncoder", "FlatApi"]
 
 
 def _sources():

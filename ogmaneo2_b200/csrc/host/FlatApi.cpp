@@ -7,7 +7,10 @@
 #include <fstream>
 #include <string>
 
+#include <ogmaneo/ImageEncoder.h>
+
 #include "../../../include/ogn_b200.h"
+#include "../../../include/ogn_image_encoder_api.h"
 #include "Device.h"
 
 using namespace ogmaneo;
@@ -439,3 +442,84 @@ int ogn_device_count(void) {
 }
 
 } // extern "C"
+
+// ---- ImageEncoder (include/ogn_image_encoder_api.h) -------------------------------------------------------------------
+namespace {
+struct IEncHandle {
+    ComputeSystem cs;
+    ImageEncoder e;
+};
+} // namespace
+extern "C" {
+const char *ogn_ienc_last_error(void) { return g_err.c_str(); }
+int ogn_ienc_create(int hx, int hy, int hz, int n, const ogn_ienc_visible_desc *d, uint32_t seed, void **out) {
+    *out = nullptr;
+    return guard([&] {
+        std::unique_ptr<IEncHandle> H(new IEncHandle());
+        H->cs.rng.seed(seed);
+        std::vector<ImageEncoder::VisibleLayerDesc> vlds((size_t)n);
+        for (int v = 0; v < n; v++) { vlds[(size_t)v].size = Int3(d[v].size_x, d[v].size_y, d[v].size_z); vlds[(size_t)v].radius = d[v].radius; }
+        H->e.initRandom(H->cs, Int3(hx, hy, hz), vlds);
+        *out = H.release();
+    });
+}
+void ogn_ienc_destroy(void *e) {
+    try { delete (IEncHandle *)e; } catch (...) {}
+}
+int ogn_ienc_step(void *e, const float *const *in, int learn) {
+    return guard([&] { IEncHandle *H = (IEncHandle *)e; H->e.stepHost(H->cs, in, learn != 0); });
+}
+int ogn_ienc_reconstruct(void *e, const int *hcs) {
+    return guard([&] { IEncHandle *H = (IEncHandle *)e; H->e.reconstructHost(H->cs, hcs); });
+}
+int ogn_ienc_hidden_cs(void *e, int *out) {
+    int n = -1;
+    guard([&] { n = copyOut(((IEncHandle *)e)->e.getHiddenCs(), out); });
+    return n;
+}
+int ogn_ienc_hidden_resources(void *e, float *out) {
+    int n = -1;
+    guard([&] { n = copyOut(((IEncHandle *)e)->e.getHiddenResources(), out); });
+    return n;
+}
+int ogn_ienc_reconstruction(void *e, int vli, float *out) {
+    int n = -1;
+    guard([&] {
+        FloatBuffer r;
+        ((IEncHandle *)e)->e.getReconstruction(vli, r);
+        n = copyOut(r, out);
+    });
+    return n;
+}
+int64_t ogn_ienc_weights(void *e, int vli, float *out, int64_t cap) {
+    int64_t n = -1;
+    guard([&] {
+        std::vector<float> w;
+        ((IEncHandle *)e)->e.getWeights(vli, w);
+        n = weightsOut(w, out, cap);
+    });
+    return n;
+}
+int ogn_ienc_set_params(void *e, float alpha, float gamma) { ((IEncHandle *)e)->e.alpha = alpha; ((IEncHandle *)e)->e.gamma = gamma; return 0; }
+int64_t ogn_ienc_save(void *e, const char *path) {
+    int64_t n = -1;
+    guard([&] {
+        std::ofstream os(path, std::ios::binary);
+        if (!os) throw std::runtime_error("cannot open file for writing");
+        ((IEncHandle *)e)->e.writeToStream(os);
+        n = (int64_t)os.tellp();
+    });
+    return n;
+}
+int ogn_ienc_load(const char *path, void **out) {
+    *out = nullptr;
+    return guard([&] {
+        std::ifstream is(path, std::ios::binary);
+        if (!is) throw std::runtime_error("cannot open file");
+        std::unique_ptr<IEncHandle> H(new IEncHandle());
+        H->e.readFromStream(is, H->cs);
+        *out = H.release();
+    });
+}
+} // extern "C"
+

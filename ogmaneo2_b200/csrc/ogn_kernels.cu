@@ -679,6 +679,220 @@ k_actor_learn(const __grid_constant__ ogn_actor_args A, const __grid_constant__ 
     }
 }
 
+// K11, latency version: one BLOCK per action column, one WARP per weight row of the column (warp 0: the value row, warp
+// 1 + hc: action row hc). A row's gather touches one weight per receptive-field slot; the lanes of the row's warp fetch
+// them all at once (one round trip through L2 instead of one per slot), and the sum is rebuilt in slot order, visible
+// layer by visible layer, with shuffles, so it is the float the sequential loop produces (Actor.cpp:105-111, :141-151).
+// The history samples of a step are still applied one after the other (a sample's gathers must see the previous sample's
+// deltas), but a sample now costs a few dependent L2 round trips instead of ~6.6 k dependent instructions.
+struct ActorRowGeo { // own field of the column inside one visible layer, seen through one matrix' packed layout
+    int lx, ly, nx, ny, lyU, nyU, Vy, Vz;
+    long long stride; // floats between consecutive (union slot, visible cell) entries of this row
+};
+__device__ __forceinline__ ActorRowGeo actor_row_geo(const ogn_rf &rf, int ox, int oy, long long rowStride) {
+    ActorRowGeo g;
+    const int q = oy / rf.pf;
+    g.lx = __ldg(rf.lox + ox); g.nx = __ldg(rf.nx + ox); g.ly = __ldg(rf.loy + oy); g.ny = __ldg(rf.ny + oy);
+    g.lyU = __ldg(rf.loyf + q); g.nyU = __ldg(rf.nyf + q); g.Vy = rf.Vy; g.Vz = rf.Vz; g.stride = rowStride;
+    return g;
+}
+// ordered sum over the field of W[row][slot][cs[slot]] (multiplyOHVs); identical on every lane
+__device__ __forceinline__ float actor_row_gather(int lane, const float *w, const int *cs, const ActorRowGeo &g) {
+    const int n = g.nx * g.ny;
+    float sum = 0.0f;
+    for (int s0 = 0; s0 < n; s0 += 32) {
+        const int s = s0 + lane;
+        float v = 0.0f;
+        if (s < n) {
+            const int dx = s / g.ny, dy = s - dx * g.ny;
+            const int c = cs[(g.lx + dx) * g.Vy + g.ly + dy];
+            v = w[((long long)(dx * g.nyU + (g.ly + dy - g.lyU)) * g.Vz + c) * g.stride];
+        }
+        const int m = min(32, n - s0);
+        for (int j = 0; j < m; ++j) sum += __shfl_sync(0xffffffffu, v, j);
+    }
+    return sum;
+}
+// W[row][slot][cs[slot]] += delta over the field (deltaOHVs): every slot is a different element, one lane each
+__device__ __forceinline__ void actor_row_delta(int lane, float *w, const int *cs, const ActorRowGeo &g, float delta) {
+    const int n = g.nx * g.ny;
+    for (int s = lane; s < n; s += 32) {
+        const int dx = s / g.ny, dy = s - dx * g.ny;
+        const int c = cs[(g.lx + dx) * g.Vy + g.ly + dy];
+        w[((long long)(dx * g.nyU + (g.ly + dy - g.lyU)) * g.Vz + c) * g.stride] += delta;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_actor_learn_rows(const __grid_constant__ ogn_actor_args A, const __grid_constant__ ogn_actor_batch B, int Hx, int Hy, int Hz,
+                   const float *__restrict__ hiddenValues, float alpha, float beta, int mimic, float *hiddenActs) {
+    __shared__ float sActs[32];
+    __shared__ float sNewValue;
+    const int col = blockIdx.x, ox = col / Hy, oy = col - ox * Hy;
+    const int row = threadIdx.x >> 5, lane = threadIdx.x & 31; // row 0: value, row 1 + hc: action cell hc
+    const bool isValue = row == 0;
+    const int hc = row - 1;
+    for (int it = 0; it < B.n; ++it) {
+        const ogn_actor_sample &S = B.it[it];
+        float sum = 0.0f;
+        int count = 0;
+        for (int v = 0; v < A.nvl; ++v) {
+            const ogn_rf &rf = A.geo[isValue ? A.vl[v].geo_v : A.vl[v].geo_a];
+            const int q = oy / rf.pf, p = oy % rf.pf;
+            const ActorRowGeo g = actor_row_geo(rf, ox, oy, isValue ? (long long)rf.pf : (long long)rf.pf * Hz);
+            const float *w = isValue ? A.vl[v].wv + f_block(rf, ox, q) + p : A.vl[v].wa + f_block(rf, ox, q) + (long long)p * Hz + hc;
+            sum += actor_row_gather(lane, w, S.cs[v], g);
+            count += g.nx * g.ny;
+        }
+        sum = div_ref(sum, (float)count);
+        if (isValue) {
+            const float newValue = S.q + S.g * hiddenValues[col];
+            if (lane == 0) sNewValue = newValue;
+            const float deltaValue = alpha * (newValue - sum);
+            for (int v = 0; v < A.nvl; ++v) {
+                const ogn_rf &rf = A.geo[A.vl[v].geo_v];
+                const int q = oy / rf.pf, p = oy % rf.pf;
+                actor_row_delta(lane, A.vl[v].wv + f_block(rf, ox, q) + p, S.cs[v], actor_row_geo(rf, ox, oy, (long long)rf.pf), deltaValue);
+            }
+        } else if (lane == 0)
+            sActs[hc] = sum;
+        __syncthreads();
+        if (!isValue) {
+            // softmax over the column's Hz activations in the reference's order (Actor.cpp:153-171): every action warp
+            // rebuilds max and total itself (lane h holds cell h), so no second block barrier is needed
+            float m = -999999.0f;
+            for (int h = 0; h < Hz; ++h) m = fmaxf(m, sActs[h]);
+            const float e = lane < Hz ? ogn_expf(sActs[lane] - m) : 0.0f;
+            float total = 0.0f;
+            for (int h = 0; h < Hz; ++h) total += __shfl_sync(0xffffffffu, e, h);
+            const float mine = __shfl_sync(0xffffffffu, e, hc);
+            const float tdErrorAction = sNewValue - S.values_prev[col];
+            const int target = S.target_prev[col];
+            const float deltaAction = (mimic ? beta : (tdErrorAction > 0.0f ? beta : -beta)) * ((hc == target ? 1.0f : 0.0f) - mine / fmaxf(0.0001f, total));
+            for (int v = 0; v < A.nvl; ++v) {
+                const ogn_rf &rf = A.geo[A.vl[v].geo_a];
+                const int q = oy / rf.pf, p = oy % rf.pf;
+                actor_row_delta(lane, A.vl[v].wa + f_block(rf, ox, q) + (long long)p * Hz + hc, S.cs[v],
+                                actor_row_geo(rf, ox, oy, (long long)rf.pf * Hz), deltaAction);
+            }
+            if (lane == 0) hiddenActs[(long long)col * Hz + hc] = mine; // hiddenActivations keeps the numerators (Actor.cpp:164)
+        }
+        __syncthreads(); // sActs / sNewValue are rewritten by the next sample; a row's weights stay with its own warp
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ImageEncoder (ImageEncoder.cpp:19-94). One pack group per hidden-y pack; lane = (column p of the pack, hidden cell). The
+// F block of a pack is read front to back: rows (union slot, visible cell) are consecutive, each holding the pack's
+// P * Hz cells, so a group's loads are contiguous 128-byte segments. Every cell keeps its own running sum in the
+// reference's order (slots x-major, then y, then visible cell; visible layer after visible layer).
+template <int G>
+__device__ __forceinline__ float ienc_distance2(const float *w, const float *in, const PackCtx &c, const ogn_rf &rf, int rowW, bool act) {
+    float d2 = 0.0f;
+    const int nxv = c.nyU > 0 ? c.nslotsU / c.nyU : 0;
+    for (int dx = 0; dx < nxv; ++dx)
+        for (int dy = 0; dy < c.nyU; ++dy) {
+            const bool own = act && (unsigned)(dy - c.dlo) < (unsigned)c.dn;
+            const float *wr = w + (long long)((dx * c.nyU + dy) * rf.Vz) * rowW;
+            const float *ir = in + (long long)rf.Vz * ((c.lyU + dy) + (long long)rf.Vy * (c.lx + dx));
+            for (int vz0 = 0; vz0 < rf.Vz; vz0 += 8) {
+                float wv[8], iv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int vz = min(vz0 + k, rf.Vz - 1);
+                    wv[k] = wr[(long long)vz * rowW];
+                    iv[k] = own ? __ldg(ir + vz) : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (own && vz0 + k < rf.Vz) { const float d = iv[k] - wv[k]; d2 += d * d; }
+            }
+        }
+    return d2;
+}
+template <int G>
+__device__ __forceinline__ void ienc_hebb(float *w, const float *in, const PackCtx &c, const ogn_rf &rf, int rowW, bool act, float strength) {
+    const int nxv = c.nyU > 0 ? c.nslotsU / c.nyU : 0;
+    for (int dx = 0; dx < nxv; ++dx)
+        for (int dy = 0; dy < c.nyU; ++dy) {
+            if (!(act && (unsigned)(dy - c.dlo) < (unsigned)c.dn)) continue;
+            float *wr = w + (long long)((dx * c.nyU + dy) * rf.Vz) * rowW;
+            const float *ir = in + (long long)rf.Vz * ((c.lyU + dy) + (long long)rf.Vy * (c.lx + dx));
+            for (int vz = 0; vz < rf.Vz; ++vz) {
+                const float old = wr[(long long)vz * rowW];
+                wr[(long long)vz * rowW] = old + strength * (__ldg(ir + vz) - old);
+            }
+        }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads)
+k_ienc_step(const __grid_constant__ ogn_ienc_args A, int Hx, int Hy, int Hz, int npacks, int packsPerRow, int learn, float alpha, float gamma,
+            float *resources, int *__restrict__ hiddenCs) {
+    constexpr int P = Pack<G>::P, GP = Pack<G>::GP;
+    const int gl = threadIdx.x & (GP - 1);
+    const int pack = (blockIdx.x * kThreads + threadIdx.x) / GP;
+    if (pack >= npacks) return;
+    const unsigned sm = lane_mask<G>();
+    const int ox = pack / packsPerRow, q = pack % packsPerRow;
+    const int p = gl / G, hc = gl % G;
+    const int oy = q * P + p;
+    const bool colValid = oy < Hy, act = colValid && hc < Hz;
+    const int hcl = hc < Hz ? hc : Hz - 1;
+    const long long col = (long long)ox * Hy + (colValid ? oy : Hy - 1);
+
+    float sum = 0.0f;
+    for (int v = 0; v < A.nvl; ++v) {
+        const ogn_rf &rf = A.geo[A.vl[v].geo];
+        const PackCtx c = pack_ctx(rf, ox, q, p);
+        sum -= ienc_distance2<G>(A.vl[v].wf + c.blk + p * Hz + hcl, A.vl[v].in, c, rf, P * Hz, act);
+    }
+    float bv = (act && sum > -999999.0f) ? sum : (act ? -999999.0f : -INFINITY);
+    int bi = act ? hc : 0x7fffffff;
+    group_argmax<G>(sm, bv, bi);
+    if (hc == 0 && colValid) hiddenCs[col] = bv > -999999.0f ? bi : 0;
+    if (!learn) return;
+    // rank of this cell among the column's cells, activations descending, equal ones in cell order (the reference sorts
+    // with a comparator on the value only; a stable order is what its sort produces whenever no two activations tie)
+    int rank = 0;
+    for (int j = 0; j < Hz; ++j) {
+        const float sj = __shfl_sync(sm, sum, j, G);
+        if (sj > sum || (sj == sum && j < hc)) rank++;
+    }
+    if (!act) return;
+    float *res = resources + col * Hz + hc;
+    const float r = *res;
+    const float strength = ogn_expf((float)(-rank * rank) * gamma / fmaxf(0.001f, r)) * r;
+    *res = r - alpha * strength;
+    for (int v = 0; v < A.nvl; ++v) {
+        const ogn_rf &rf = A.geo[A.vl[v].geo];
+        const PackCtx c = pack_ctx(rf, ox, q, p);
+        ienc_hebb<G>(A.vl[v].wf + c.blk + p * Hz + hcl, A.vl[v].in, c, rf, P * Hz, act, strength);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_ienc_reconstruct(const __grid_constant__ ogn_ienc_args A, int vli, int Hy, int Hz, const int *__restrict__ hcs) {
+    const ogn_rf &rf = A.geo[A.vl[vli].geo];
+    const long long n = (long long)rf.Vx * rf.Vy * rf.Vz;
+    const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const int vz = (int)(i % rf.Vz);
+    const int iy = (int)((i / rf.Vz) % rf.Vy), ix = (int)(i / ((long long)rf.Vz * rf.Vy));
+    const int hx0 = __ldg(rf.rlox + ix), hx1 = __ldg(rf.rhix + ix), hy0 = __ldg(rf.rloy + iy), hy1 = __ldg(rf.rhiy + iy);
+    float sum = 0.0f;
+    int count = 0;
+    for (int ox = hx0; ox <= hx1; ++ox)
+        for (int oy = hy0; oy <= hy1; ++oy) {
+            const int q = oy / rf.pf, p = oy % rf.pf;
+            const int su = (ix - __ldg(rf.lox + ox)) * __ldg(rf.nyf + q) + (iy - __ldg(rf.loyf + q));
+            const int hc = __ldg(hcs + ox * Hy + oy);
+            sum += A.vl[vli].wf[f_block(rf, ox, q) + ((long long)(su * rf.Vz + vz) * rf.pf + p) * Hz + hc];
+            count++;
+        }
+    A.vl[vli].recon[i] = sum / (float)max(1, count);
+}
+
 #include "ogn_vec.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1155,6 +1369,28 @@ int ogn_pred_step(const ogn_pred_args *args, int Hx, int Hy, int Hz, int x0, int
     return launch_status();
 }
 
+int ogn_image_encoder_step(const ogn_ienc_args *args, int Hx, int Hy, int Hz, int learn, float alpha, float gamma, float *resources, int *hidden_cs,
+                  void *stream) {
+    if (args->nvl <= 0 || args->nvl > OGN_MAX_IENC_VL || Hz > 32 || Hz <= 0) return (int)cudaErrorInvalidValue;
+    const int g = group_lanes(Hz), P = pack_factor(g), ppr = (Hy + P - 1) / P, npacks = Hx * ppr;
+    for (int v = 0; v < args->nvl; v++)
+        if (args->geo[args->vl[v].geo].pf != P) return (int)cudaErrorInvalidValue;
+    if (npacks <= 0) return 0;
+    dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads));
+    OGN_DISPATCH_G(g, (k_ienc_step<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, npacks, ppr, learn, alpha, gamma, resources,
+                                                                                hidden_cs)));
+    return launch_status();
+}
+
+int ogn_image_encoder_reconstruct(const ogn_ienc_args *args, int vli, int Hx, int Hy, int Hz, const int *hidden_cs, void *stream) {
+    if (vli < 0 || vli >= args->nvl) return (int)cudaErrorInvalidValue;
+    const ogn_rf &rf = args->geo[args->vl[vli].geo];
+    const long long n = (long long)rf.Vx * rf.Vy * rf.Vz;
+    if (n <= 0) return 0;
+    k_ienc_reconstruct<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(*args, vli, Hy, Hz, hidden_cs);
+    return launch_status();
+}
+
 int ogn_hier_small_max_blocks(int threads) {
     int dev = 0, sms = 0, per = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -1200,6 +1436,12 @@ int ogn_actor_learn(const ogn_actor_args *args, const ogn_actor_batch *batch, in
                     float alpha, float beta, int mimic, float *hidden_activations, void *stream) {
     if (args->nvl > OGN_MAX_PRED_VL || batch->n < 0 || batch->n > OGN_MAX_ACTOR_SAMPLES) return (int)cudaErrorInvalidValue;
     if (batch->n == 0) return 0;
+    static const int rowsKernel = env_int("OGN_ACTOR_ROWS", 1);
+    if (rowsKernel && Hz <= 31) { // one block per action column, one warp per weight row
+        k_actor_learn_rows<<<(unsigned)(Hx * Hy), 32 * (1 + Hz), 0, (cudaStream_t)stream>>>(*args, *batch, Hx, Hy, Hz, hidden_values, alpha, beta,
+                                                                                       mimic, hidden_activations);
+        return launch_status();
+    }
     const int g = group_lanes(Hz), P = pack_factor(g), ppr = (Hy + P - 1) / P, npacks = Hx * ppr;
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads));
     OGN_DISPATCH_G(g, (k_actor_learn<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, *batch, Hx, Hy, Hz, npacks, ppr, hidden_values,

@@ -48,12 +48,13 @@ def _stamp(target, sources):
 def build(verbose=False):
     """Compile the port always (if stale) and oracle/_ref when the reference sources are present."""
     out = None if verbose else subprocess.DEVNULL
-    srcs = [os.path.join(HERE, "sph_oracle.cpp"), os.path.join(HERE, "..", "include", "ogn_hierarchy_api.h")]
+    srcs = [os.path.join(HERE, "sph_oracle.cpp"), os.path.join(HERE, "..", "include", "ogn_hierarchy_api.h"),
+            os.path.join(HERE, "ienc_oracle.cpp"), os.path.join(HERE, "..", "include", "ogn_image_encoder_api.h")]
     if _stale(PORT_SO, srcs):
         subprocess.check_call(["make", "-B", "-C", HERE, "port"], stdout=out)
         _stamp(PORT_SO, srcs)
     if os.path.isdir(os.path.join(REF_SRC, "source", "ogmaneo")):
-        rsrcs = [os.path.join(HERE, "ref_shim.cpp"), srcs[1]]
+        rsrcs = [os.path.join(HERE, "ref_shim.cpp"), srcs[1], srcs[3]]
         if _stale(REF_SO, rsrcs):
             subprocess.check_call(["make", "-C", HERE, "ref", f"REF={REF_SRC}"], stdout=out)
             _stamp(REF_SO, rsrcs)

@@ -24,9 +24,11 @@
 // tests compare them, so open the classes up for this one translation unit (layout is unaffected).
 #define private public
 #include <ogmaneo/Hierarchy.h>
+#include <ogmaneo/ImageEncoder.h>
 #undef private
 
 #include "../include/ogn_hierarchy_api.h"
+#include "../include/ogn_image_encoder_api.h"
 
 using namespace ogmaneo; // == ogmaneo_ref after macro renaming
 
@@ -210,3 +212,81 @@ uint32_t oref_rng_peek(void *h) {
     return (uint32_t)c();
 }
 } // extern "C"
+
+// ---- ImageEncoder (ImageEncoder.h / ImageEncoder.cpp) through include/ogn_image_encoder_api.h, prefix oref_ --------------
+namespace {
+struct IEnc {
+    ComputeSystem cs;
+    ImageEncoder e;
+};
+} // namespace
+extern "C" {
+OGN_DECLARE_IMAGE_ENCODER_API(oref_)
+int oref_ienc_create(int hx, int hy, int hz, int n, const ogn_ienc_visible_desc *d, uint32_t seed, void **out) {
+    try {
+        auto *E = new IEnc();
+        E->cs.rng.seed(seed);
+        std::vector<ImageEncoder::VisibleLayerDesc> vlds((size_t)n);
+        for (int v = 0; v < n; v++) {
+            vlds[(size_t)v].size = Int3(d[v].size_x, d[v].size_y, d[v].size_z);
+            vlds[(size_t)v].size.pad = 0;
+            vlds[(size_t)v].radius = d[v].radius;
+        }
+        Int3 hs(hx, hy, hz);
+        hs.pad = 0;
+        E->e.initRandom(E->cs, hs, vlds);
+        *out = E;
+        return 0;
+    } catch (const std::exception &ex) {
+        return fail(ex.what());
+    }
+}
+void oref_ienc_destroy(void *e) { delete (IEnc *)e; }
+const char *oref_ienc_last_error(void) { return g_err.c_str(); }
+int oref_ienc_step(void *ee, const float *const *in, int learn) {
+    IEnc *E = (IEnc *)ee;
+    const int n = E->e.getNumVisibleLayers();
+    std::vector<FloatBuffer> bufs((size_t)n);
+    std::vector<const FloatBuffer *> ptrs((size_t)n);
+    for (int v = 0; v < n; v++) {
+        const Int3 &s = E->e.getVisibleLayerDesc(v).size;
+        bufs[(size_t)v].assign(in[v], in[v] + (size_t)s.x * s.y * s.z);
+        ptrs[(size_t)v] = &bufs[(size_t)v];
+    }
+    E->e.step(E->cs, ptrs, learn != 0);
+    return 0;
+}
+int oref_ienc_reconstruct(void *ee, const int *hcs) {
+    IEnc *E = (IEnc *)ee;
+    const Int3 &s = E->e.getHiddenSize();
+    IntBuffer b(hcs, hcs + (size_t)s.x * s.y);
+    E->e.reconstruct(E->cs, &b);
+    return 0;
+}
+int oref_ienc_hidden_cs(void *e, int *out) { return copyOut(((IEnc *)e)->e.getHiddenCs(), out); }
+int oref_ienc_hidden_resources(void *e, float *out) { return copyOut(((IEnc *)e)->e.hiddenResources, out); }
+int oref_ienc_reconstruction(void *e, int vli, float *out) { return copyOut(((IEnc *)e)->e.getVisibleLayer(vli).reconstructions, out); }
+int64_t oref_ienc_weights(void *e, int vli, float *out, int64_t cap) {
+    return copyW(((IEnc *)e)->e.getVisibleLayer(vli).weights.nonZeroValues, out, cap);
+}
+int oref_ienc_set_params(void *e, float alpha, float gamma) { ((IEnc *)e)->e.alpha = alpha; ((IEnc *)e)->e.gamma = gamma; return 0; }
+int64_t oref_ienc_save(void *e, const char *path) {
+    std::ofstream os(path, std::ios::binary);
+    if (!os) return -1;
+    // the reference leaves Int3::pad uninitialised: zero the pads of the descriptors so that files compare
+    IEnc *E = (IEnc *)e;
+    E->e.hiddenSize.pad = 0;
+    for (auto &d : E->e.visibleLayerDescs) d.size.pad = 0;
+    E->e.writeToStream(os);
+    return (int64_t)os.tellp();
+}
+int oref_ienc_load(const char *path, void **out) {
+    std::ifstream is(path, std::ios::binary);
+    if (!is) return fail("cannot open file");
+    auto *E = new IEnc();
+    E->e.readFromStream(is);
+    *out = E;
+    return 0;
+}
+} // extern "C"
+

@@ -9,11 +9,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = set()
-    for f in ("ogn_hierarchy_api.h", "ogn_b200.h", "ogn_kernels_api.h"):
+    for f in ("ogn_hierarchy_api.h", "ogn_b200.h", "ogn_kernels_api.h", "ogn_image_encoder_api.h"):
         text = open(os.path.join(ROOT, "include", f)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names |= set(re.findall(r"\b(ogn_[a-z0-9_]+)\s*\(", text))
-        if f == "ogn_hierarchy_api.h":
+        if f in ("ogn_hierarchy_api.h", "ogn_image_encoder_api.h"):
             names |= {"ogn_" + m for m in re.findall(r"P##([a-z0-9_]+)\s*\(", text)}
     return {n for n in names if not n.endswith("_fn")}
 
