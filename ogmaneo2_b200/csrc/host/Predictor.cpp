@@ -1,6 +1,8 @@
 // csrc/host/Predictor.cpp — ogmaneo::Predictor on the device (public interface: include/ogmaneo/Predictor.h).
 #include "LayerImpl.h"
 
+#include <cstdlib>
+
 namespace ogmaneo {
 using namespace detail;
 
@@ -109,9 +111,20 @@ void Predictor::stepDevice(ComputeSystem &cs, bool learn, const int *targetDev, 
         ctx.collect->ok = ctx.collect->ok && ok;
         ctx.collect->add(P);
     } else {
+    // OGN_PRED_SPLIT=1 (experiment, profiles/README.md): the learn pass (a pure read-modify-write of 128-byte lines) and the
+    // activate pass (a pure gather) as two launches instead of one kernel that mixes reads and writes 2:1
+    static const bool split = [] { const char *e = std::getenv("OGN_PRED_SPLIT"); return e && std::atoi(e) != 0; }();
+    if (split && learn && activate) {
+        { LaunchScope ls(ctx, kPredStep, st);
+        if (!ctx.dry) kernelCheck(ogn_pred_step(&a, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, 1, 0, targetDev, alpha,
+                                  m.acts.ptr(), m.hiddenCs.ptr(), st), "pred_step(learn)"); }
+        { LaunchScope ls(ctx, kPredStep, st);
+        if (!ctx.dry) kernelCheck(ogn_pred_step(&a, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, 0, 1, targetDev, alpha,
+                                  m.acts.ptr(), m.hiddenCs.ptr(), st), "pred_step(activate)"); }
+    } else {
     LaunchScope ls(ctx, kPredStep, st);
     if (!ctx.dry) kernelCheck(ogn_pred_step(&a, hiddenSize.x, hiddenSize.y, hiddenSize.z, m.x0, m.x1, m.batch, learn ? 1 : 0, activate ? 1 : 0,
-                              targetDev, alpha, m.acts.ptr(), m.hiddenCs.ptr(), st), "pred_step"); }
+                              targetDev, alpha, m.acts.ptr(), m.hiddenCs.ptr(), st), "pred_step"); } }
     if (learn) std::fill(m.wDirty.begin(), m.wDirty.end(), 1);
     if (activate) {
         m.prevCur = 1 - m.prevCur;

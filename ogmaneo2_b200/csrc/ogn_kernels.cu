@@ -781,6 +781,50 @@ k_actor_learn_rows(const __grid_constant__ ogn_actor_args A, const __grid_consta
     }
 }
 
+// K9 in the same mapping (Actor::forward, Actor.cpp:13-90): value row and action rows gathered by one warp each, softmax and
+// the sampling scan on the action warps (every one of them rebuilds the column's numerators; warp 1 writes the result).
+__global__ void __launch_bounds__(1024)
+k_actor_forward_rows(const __grid_constant__ ogn_actor_args A, int Hx, int Hy, int Hz, const float *__restrict__ u01, float *hiddenValues,
+                     float *hiddenActs, int *hiddenCs) {
+    __shared__ float sActs[32];
+    const int col = blockIdx.x, ox = col / Hy, oy = col - ox * Hy;
+    const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool isValue = row == 0;
+    const int hc = row - 1;
+    float sum = 0.0f;
+    int count = 0;
+    for (int v = 0; v < A.nvl; ++v) {
+        const ogn_rf &rf = A.geo[isValue ? A.vl[v].geo_v : A.vl[v].geo_a];
+        const int q = oy / rf.pf, p = oy % rf.pf;
+        const ActorRowGeo g = actor_row_geo(rf, ox, oy, isValue ? (long long)rf.pf : (long long)rf.pf * Hz);
+        const float *w = isValue ? A.vl[v].wv + f_block(rf, ox, q) + p : A.vl[v].wa + f_block(rf, ox, q) + (long long)p * Hz + hc;
+        sum += actor_row_gather(lane, w, A.vl[v].cs, g);
+        count += g.nx * g.ny;
+    }
+    sum = div_ref(sum, (float)count);
+    if (isValue) { if (lane == 0) hiddenValues[col] = sum; }
+    else if (lane == 0) sActs[hc] = sum;
+    __syncthreads();
+    if (isValue) return;
+    float m = -999999.0f;
+    for (int h = 0; h < Hz; ++h) m = fmaxf(m, sActs[h]);
+    const float e = lane < Hz ? ogn_expf(sActs[lane] - m) : 0.0f;
+    float total = 0.0f;
+    for (int h = 0; h < Hz; ++h) total += __shfl_sync(0xffffffffu, e, h);
+    if (hc != 0) return; // one writer per column
+    if (lane < Hz) hiddenActs[(long long)col * Hz + lane] = e; // hiddenActivations keeps the numerators (Actor.cpp:66)
+    // std::uniform_real_distribution<float>(0, total): canonical * (b - a) + a   (libstdc++ bits/random.h)
+    const float cusp = u01[col] * (total - 0.0f) + 0.0f;
+    int select = 0;
+    float sumSoFar = 0.0f;
+    bool found = false;
+    for (int h = 0; h < Hz; ++h) {
+        sumSoFar += __shfl_sync(0xffffffffu, e, h);
+        if (!found && sumSoFar >= cusp) { select = h; found = true; }
+    }
+    if (lane == 0) hiddenCs[col] = select;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // ImageEncoder (ImageEncoder.cpp:19-94). One pack group per hidden-y pack; lane = (column p of the pack, hidden cell). The
 // F block of a pack is read front to back: rows (union slot, visible cell) are consecutive, each holding the pack's
@@ -1425,6 +1469,12 @@ int ogn_hier_step_small(const ogn_small_phase *phases, int nphases, const ogn_sm
 int ogn_actor_forward(const ogn_actor_args *args, int Hx, int Hy, int Hz, const float *u01, float *hidden_values,
                       float *hidden_activations, int *hidden_cs, void *stream) {
     if (args->nvl > OGN_MAX_PRED_VL) return (int)cudaErrorInvalidValue;
+    static const int rowsKernel = env_int("OGN_ACTOR_ROWS", 1);
+    if (rowsKernel && Hz <= 31) { // one block per action column, one warp per weight row
+        k_actor_forward_rows<<<(unsigned)(Hx * Hy), 32 * (1 + Hz), 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, u01, hidden_values,
+                                                                                         hidden_activations, hidden_cs);
+        return launch_status();
+    }
     const int g = group_lanes(Hz), P = pack_factor(g), ppr = (Hy + P - 1) / P, npacks = Hx * ppr;
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads));
     OGN_DISPATCH_G(g, (k_actor_forward<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, npacks, ppr, u01, hidden_values,

@@ -221,16 +221,45 @@ __device__ __forceinline__ void sc_forward_pack(const ogn_fwd_args &A, int Hx, i
     const unsigned om = octet_mask();
     const PackId id = pack_id<Z>(pack, packsPerRow, x0, Hy, sub);
     float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    for (int v = 0; v < A.nvl; ++v) {
-        const ogn_fwd_vl &vl = A.vl[v];
-        const ogn_rf &rf = A.geo[vl.geo];
-        const PackCtx c = pack_ctx(rf, id.ox, id.q, id.p);
-        const float *wl = vl.wf + (c.blk + (long long)member * vl.mstride) + sub * 4;
-        CsView cv;
-        if (tiles) cv = tiles[v];
-        else { cv.p = vl.cs + (long long)member * rf.Vx * rf.Vy; cv.rs = rf.Vy; }
-        const float4 g = gather<true, NCH, W, CS>(om, sub, oct, wl, cv.p, cv.rs, c, rf.Vz);
-        sum.x += g.x; sum.y += g.y; sum.z += g.z; sum.w += g.w;
+    if (W == 32 && A.nvl >= 3) {
+        // wide mapping with several visible layers (temporalHorizon x inputs): the reference sums every visible layer into
+        // its own accumulator and adds the results in layer order (SparseCoder.cpp:23-40), so the four octets of the warp
+        // each take ONE visible layer (a whole octet-per-pack gather, 16 lines in flight per lane) and the per-layer sums
+        // are combined in order afterwards: the layers' dependent chains (tables, CSDR, weights) run side by side
+        // instead of one after the other.
+        for (int base = 0; base < A.nvl; base += 4) {
+            const int v = base + oct;
+            float4 g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (v < A.nvl) {
+                const ogn_fwd_vl &vl = A.vl[v];
+                const ogn_rf &rf = A.geo[vl.geo];
+                const PackCtx c = pack_ctx(rf, id.ox, id.q, id.p);
+                const float *wl = vl.wf + (c.blk + (long long)member * vl.mstride) + sub * 4;
+                CsView cv;
+                if (tiles) cv = tiles[v];
+                else { cv.p = vl.cs + (long long)member * rf.Vx * rf.Vy; cv.rs = rf.Vy; }
+                g = gather<true, 2, 8, CS>(om, sub, 0, wl, cv.p, cv.rs, c, rf.Vz);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (base + o < A.nvl) {
+                    const float4 t = shfl4(0xffffffffu, g, o * 8 + sub);
+                    sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+                }
+        }
+    } else {
+        for (int v = 0; v < A.nvl; ++v) {
+            const ogn_fwd_vl &vl = A.vl[v];
+            const ogn_rf &rf = A.geo[vl.geo];
+            const PackCtx c = pack_ctx(rf, id.ox, id.q, id.p);
+            const float *wl = vl.wf + (c.blk + (long long)member * vl.mstride) + sub * 4;
+            CsView cv;
+            if (tiles) cv = tiles[v];
+            else { cv.p = vl.cs + (long long)member * rf.Vx * rf.Vy; cv.rs = rf.Vy; }
+            const float4 g = gather<true, NCH, W, CS>(om, sub, oct, wl, cv.p, cv.rs, c, rf.Vz);
+            sum.x += g.x; sum.y += g.y; sum.z += g.z; sum.w += g.w;
+        }
     }
     const int best = column_argmax_fwd<Z>(om, id.hz0, sum);
     if (id.hz0 == 0 && id.colValid && (W == 8 || oct == 0)) {
