@@ -3,6 +3,7 @@
 #include "LayerImpl.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cassert>
 #include <map>
 
@@ -323,7 +324,8 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
     // Sharded layers: the learn pass of the layer-0 Predictors needs nothing this step produces (its target is the
     // input just copied, its gather rows are last step's inputs), so it is hoisted to the side stream and runs while the
     // main stream does the SparseCoder forward pass and its slab exchange; the activate pass follows on the main stream.
-    const bool hoistPredLearn = ctx.useSide && learnEnabled && !cs.replayRng;
+    static const bool hoistAllowed = [] { const char *e = std::getenv("OGN_PRED_HOIST"); return !e || std::atoi(e) != 0; }();
+    const bool hoistPredLearn = hoistAllowed && ctx.useSide && learnEnabled && !cs.replayRng;
     bool predLearnPending = false;
     if (hoistPredLearn) {
         bool any = false;
