@@ -84,11 +84,11 @@ uint64_t ogn_take_sc_update_count(void *h, int l);
 /* Launch accounting. Kernel kinds, in array order: 0 SparseCoder forward (K2), 1 SparseCoder learn (K3: the
  * reconstruction when learn runs as two kernels, else the fused learn), 2 Predictor learn+activate (K6+K7+K8), 3 Actor
  * forward (K9), 4 Actor learn (K11), 5 SparseCoder learn part 2 (work-list update), 6 the single-launch small-hierarchy step
- * (every phase of a step in one kernel, ogn_hier_step_small). enable(on) resets the counters; with on != 0
+ * (every phase of a step in one kernel, ogn_hier_step_small), 7 the peer-memory CSDR exchange of sharded layers. enable(on) resets the counters; with on != 0
  * the launches of every on-th Hierarchy::step (on = 1: every step) are bracketed by CUDA events on the stream they are
  * queued on. read() synchronises and returns, per kind (arrays of OGN_KERNEL_KINDS): the device milliseconds summed
  * over the bracketed launches, the number of launches, and the number of bracketed launches. */
-#define OGN_KERNEL_KINDS 7
+#define OGN_KERNEL_KINDS 8
 int ogn_profile_enable(void *h, int on);
 int ogn_profile_read(void *h, double *ms, int64_t *launches, int64_t *timed_launches);
 int ogn_device_count(void);

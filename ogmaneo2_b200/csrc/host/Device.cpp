@@ -2,6 +2,7 @@
 #include "Device.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -144,7 +145,8 @@ void DeviceContext::peerAllGather(int *buffer, int countPerRank, bool deferred, 
     const unsigned everybody = (a.world >= 32 ? 0xffffffffu : ((1u << a.world) - 1u)) & ~(1u << a.rank);
     static const bool haloWait = [] { const char *e = std::getenv("OGN_PEER_HALO_WAIT"); return !e || std::atoi(e) != 0; }();
     const unsigned mask = (waitMask && haloWait) ? (waitMask & everybody) : everybody;
-    kernelCheck(ogn_peer_allgather(&t, buffer - a.base, countPerRank, ++a.epoch, mask, timeoutNs, a.errDev, st), "peer_allgather");
+    { LaunchScope ls(*this, kExchange, st);
+    kernelCheck(ogn_peer_allgather(&t, buffer - a.base, countPerRank, ++a.epoch, mask, timeoutNs, a.errDev, st), "peer_allgather"); }
     if (deferred) exchangeQueued();
 }
 
@@ -189,6 +191,21 @@ cudaEvent_t DeviceContext::takeEvent() {
 void DeviceContext::profileCollect() {
     sync();
     peerCheck();
+    // OGN_TIMELINE=n: print the first n bracketed launches as a timeline (kind, stream, start relative to the first one,
+    // duration; microseconds) to stderr: where a sharded step's time goes across the two streams
+    static int timeline = [] { const char *e = std::getenv("OGN_TIMELINE"); return e ? std::atoi(e) : 0; }();
+    if (timeline > 0 && !recs.empty()) {
+        static const char *names[kKernelKinds] = {"sc_forward", "sc_recon", "pred_step", "actor_fwd", "actor_learn", "sc_update", "hier_small", "exchange"};
+        const size_t skip = recs.size() > (size_t)timeline * 2 ? recs.size() / 2 : 0; // a step from the middle of the region
+        for (size_t i = skip; i < recs.size() && i < skip + (size_t)timeline; i++) {
+            float t0 = 0.0f, dt = 0.0f;
+            cudaEventElapsedTime(&t0, recs[skip].a, recs[i].a);
+            cudaEventElapsedTime(&dt, recs[i].a, recs[i].b);
+            std::fprintf(stderr, "[ogn timeline] dev %d %-11s %s start %9.1f us  dur %7.1f us\n", device, names[recs[i].kind],
+                         recs[i].onSide ? "side" : "main", t0 * 1e3f, dt * 1e3f);
+        }
+        timeline = 0;
+    }
     for (auto &r : recs) {
         float ms = 0.0f;
         cudaCheck(cudaEventElapsedTime(&ms, r.a, r.b), "cudaEventElapsedTime");

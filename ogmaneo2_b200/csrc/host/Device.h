@@ -24,7 +24,7 @@ namespace detail {
 void cudaCheck(cudaError_t e, const char *what);
 inline void kernelCheck(int code, const char *what) { cudaCheck((cudaError_t)code, what); }
 
-enum KernelKind { kScForward = 0, kScLearn = 1, kPredStep = 2, kActorForward = 3, kActorLearn = 4, kScUpdate = 5, kHierSmall = 6, kKernelKinds = 7 };
+enum KernelKind { kScForward = 0, kScLearn = 1, kPredStep = 2, kActorForward = 3, kActorLearn = 4, kScUpdate = 5, kHierSmall = 6, kExchange = 7, kKernelKinds = 8 };
 
 // Phases of one Hierarchy::step recorded instead of launched (DeviceContext::collect): the single-launch small-hierarchy
 // kernel runs them from a device-resident array (ogn_hier_step_small). layer / role let Hierarchy::step order them into
@@ -107,10 +107,10 @@ struct DeviceContext {
     long long profileStep = 0;
     bool sampleThis = true;
     void beginStep() { sampleThis = profiling && (profileStep++ % (profilePeriod > 0 ? profilePeriod : 1)) == 0; }
-    long long timedLaunches[kKernelKinds] = {0, 0, 0, 0, 0, 0, 0};
-    long long launches[kKernelKinds] = {0, 0, 0, 0, 0, 0, 0};
-    double kernelMs[kKernelKinds] = {0, 0, 0, 0, 0, 0, 0};
-    struct Rec { cudaEvent_t a, b; int kind; };
+    long long timedLaunches[kKernelKinds] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long launches[kKernelKinds] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double kernelMs[kKernelKinds] = {0, 0, 0, 0, 0, 0, 0, 0};
+    struct Rec { cudaEvent_t a, b; int kind; int onSide; };
     std::vector<Rec> recs;
     std::vector<cudaEvent_t> eventPool;
     cudaEvent_t takeEvent();
@@ -133,7 +133,7 @@ struct LaunchScope {
         if (a) {
             cudaEvent_t b = c.takeEvent();
             cudaEventRecord(b, st);
-            c.recs.push_back(DeviceContext::Rec{a, b, kind});
+            c.recs.push_back(DeviceContext::Rec{a, b, kind, st == c.side ? 1 : 0});
         }
     }
 };

@@ -189,7 +189,7 @@ class Hierarchy(FlatHierarchy):
     def synchronize(self):
         self._chk(self.f.synchronize(self.h), "synchronize")
 
-    KERNEL_KINDS = ("sc_forward", "sc_learn", "pred_step", "actor_forward", "actor_learn", "sc_update", "hier_small")
+    KERNEL_KINDS = ("sc_forward", "sc_learn", "pred_step", "actor_forward", "actor_learn", "sc_update", "hier_small", "exchange")
 
     def profileEnable(self, on=True, period: int = 1):
         """Count launches; time (CUDA events) the launches of every period-th step."""
