@@ -161,7 +161,7 @@ void SparseCoder::stepDevice(ComputeSystem &cs, const int *const *inputCsDev, bo
                 P.work = la.work; P.workStride = (int64_t)(m.runOffset[run + 1] - m.runOffset[run]);
                 P.updCount = m.upd.ptr();
                 P.counter = ctx.collect->lists++;
-                P.updVer = ogn_sc_update_version(&la); P.chunks = ogn_sc_update_chunks(&la, P.updVer); P.updBatches = ogn_sc_update_batches();
+                P.updVer = std::min(2, ogn_sc_update_version(&la)); P.chunks = ogn_sc_update_chunks(&la, P.updVer); P.updBatches = ogn_sc_update_batches();
                 const bool ok = ogn_vec_row_ok(Vz) != 0 && ogn_vec_geo_ok(&la.geo) != 0 && !sharded && P.counter < OGN_SMALL_MAX_LISTS &&
                                 P.chunks > 0;
                 ctx.collect->ok = ctx.collect->ok && ok;

@@ -1258,6 +1258,7 @@ int ogn_sc_update_version(const ogn_learn_args *args) {
     // default: version 1. Version 2 (full 32-byte sector stores into F) was measured on B200 (profiles/README.md): the L2
     // still fills the sector from DRAM (the DRAM-side write atom is 64 bytes), so it only adds the R group reads.
     if (forced == 2) return v2ok ? 2 : 1;
+    if (forced == 3) return args->geo.Hz % 16 == 0 ? 3 : (v2ok ? 2 : 1); // groups of 16 hidden cells: full 64-byte stores
     return 1;
 }
 int ogn_sc_update_batches(void) {
@@ -1267,7 +1268,9 @@ int ogn_sc_update_batches(void) {
 }
 int ogn_sc_update_chunks(const ogn_learn_args *args, int version) {
     const int Vz = args->geo.Vz;
-    const int items = version == 2 ? ((2 * Vz >= 32 ? 1 : 32 / (2 * Vz)) * 4) * ogn_sc_update_batches() : (32 / (Vz / 4)) * 4;
+    int items = (32 / (Vz / 4)) * 4;
+    if (version == 2) items = ((2 * Vz >= 32 ? 1 : 32 / (2 * Vz)) * 4) * ogn_sc_update_batches();
+    if (version == 3) items = ((4 * Vz >= 32 ? 1 : 32 / (4 * Vz)) * 2) * ogn_sc_update_batches();
     return (args->geo.max_cov + items - 1) / items;
 }
 
@@ -1350,7 +1353,11 @@ int ogn_sc_learn(const ogn_learn_args *args, const int *hidden_cs, const int *hi
         long long maxUnits = (long long)(vx1 - vx0) * args->geo.Vy * batch * args->nvl * chunks;
         long long blocks = (maxUnits + (kThreads / 32) - 1) / (kThreads / 32);
         if (blocks > update_grid_blocks()) blocks = update_grid_blocks();
-        if (ver == 2) {
+        if (ver == 3) {
+            OGN_DISPATCH_Z(Vz, (vec::k_sc_update_v<Z, 3><<<(unsigned)blocks, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, work, cnt,
+                                                                                             cnt + 1, alpha, update_count, chunks,
+                                                                                             ogn_sc_update_batches())));
+        } else if (ver == 2) {
             OGN_DISPATCH_Z(Vz, (vec::k_sc_update_v<Z, 2><<<(unsigned)blocks, kThreads, 0, st>>>(*args, hidden_cs, hidden_cs_prev, work, cnt,
                                                                                              cnt + 1, alpha, update_count, chunks,
                                                                                              ogn_sc_update_batches())));

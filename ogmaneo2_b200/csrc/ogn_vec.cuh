@@ -568,10 +568,10 @@ __device__ __forceinline__ int sc_update_unit_v1(const ogn_learn_args &A, const 
 // lane stores its 4 values into F with 4 scalar stores whose 8 lanes per forward row cover exactly one 32-byte sector:
 // no sector is partially written, so the L2 never reads F (no fill, half the row activations), and the F writes carry
 // the group's unchanged cells, which are bit-identical in both copies (invariant checked by ogn_weights_fr_mismatch).
-template <int Z, class CS, bool kCg>
+template <int Z, int GRP, class CS, bool kCg>
 __device__ __forceinline__ int sc_update_unit_v2(const ogn_learn_args &A, const int *hcsAll, const int *hcsPrevAll, const int2 wk, int k0,
                                                  int batches, float alpha) {
-    constexpr int LC = Z / 4, SL = 8 * LC, PPI = SL >= 32 ? 1 : 32 / SL, J = SL >= 32 ? SL / 32 : 1, PR = 32 / Z, UN = 4;
+    constexpr int LC = Z / 4, SL = GRP * LC, PPI = SL >= 32 ? 1 : 32 / SL, J = SL >= 32 ? SL / 32 : 1, PR = 32 / Z, UN = GRP == 8 ? 4 : 2;
     const ogn_rf &rf = A.geo;
     const int lane = threadIdx.x & 31;
     const long long fstep = (long long)rf.pf * rf.Hz;
@@ -594,7 +594,7 @@ __device__ __forceinline__ int sc_update_unit_v2(const ogn_learn_args &A, const 
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         const int sl = (PPI > 1 ? lane % SL : lane) + 32 * j;
-        hz8[j] = sl / LC; q4[j] = (sl % LC) * 4;
+        hz8[j] = sl % GRP; q4[j] = (sl / GRP) * 4; // the GRP lanes of one forward row are neighbours: one store instruction, one full granule
     }
     // delta of the visible cells of this lane's slices (SparseCoder.cpp:78): once per unit, shared by all its pairs
     const int target = CS::ld(vl.cs + vcol);
@@ -625,7 +625,7 @@ __device__ __forceinline__ int sc_update_unit_v2(const ogn_learn_args &A, const 
                 if (hc != CS::ld(hcsPrev + h)) {
                     const int ylo = __ldg(rf.loy + oy);
                     const int dx = vx - __ldg(rf.lox + ox);
-                    const int g8 = hc & ~7;
+                    const int g8 = hc & ~(GRP - 1);
                     // R row of hidden cell g8 (the group's first), this visible column; consecutive hidden cells: + PR * Z floats
                     offR[u] = r_block(rf, ox, oy) +
                               ((((long long)dx * __ldg(rf.ngr + oy) + (vy / PR - ylo / PR)) * rf.Hz + g8) * PR + (vy % PR)) * Z;
@@ -634,7 +634,7 @@ __device__ __forceinline__ int sc_update_unit_v2(const ogn_learn_args &A, const 
                     offF[u] = f_block(rf, ox, qh) +
                               (((long long)dx * __ldg(rf.nyf + qh) + (vy - __ldg(rf.loyf + qh))) * Z * rf.pf + ph) * rf.Hz + g8;
                     fl[u] = 1 | ((ox >= A.fx0 && ox < A.fx1) ? 2 : 0);
-                    hcl[u] = hc & 7;
+                    hcl[u] = hc & (GRP - 1);
                 }
             }
         }
@@ -663,8 +663,8 @@ __device__ __forceinline__ int sc_update_unit_v2(const ogn_learn_args &A, const 
     }
     return nupd;
 }
-template <int Z> struct UpdV2 {
-    static constexpr int SL = 2 * Z, PPI = SL >= 32 ? 1 : 32 / SL, ITEMS = PPI * 4; // cover items per batch; a unit is `batches` of them
+template <int Z, int GRP = 8> struct UpdV2 {
+    static constexpr int SL = GRP * Z / 4, PPI = SL >= 32 ? 1 : 32 / SL, ITEMS = PPI * (GRP == 8 ? 4 : 2); // cover items per batch; a unit is `batches` of them
 };
 template <int Z> struct UpdV1 {
     static constexpr int ITEMS = (32 / (Z / 4)) * 4;
@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(kThreads)
 k_sc_update_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ hcsAll, const int *__restrict__ hcsPrevAll,
               const int2 *__restrict__ work, unsigned *workCount, unsigned *doneCount, float alpha, unsigned long long *updCount,
               int chunksPerEntry, int batches) {
-    const int ITEMS = VER == 2 ? UpdV2<Z>::ITEMS * batches : UpdV1<Z>::ITEMS;
+    const int ITEMS = VER == 3 ? UpdV2<Z, 16>::ITEMS * batches : VER == 2 ? UpdV2<Z, 8>::ITEMS * batches : UpdV1<Z>::ITEMS;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
     const unsigned n = *(volatile unsigned *)workCount;
@@ -852,7 +852,8 @@ k_sc_update_v(const __grid_constant__ ogn_learn_args A, const int *__restrict__ 
         const unsigned e = (unsigned)(unit / (unsigned)chunksPerEntry);
         const int k0 = (int)(unit - (unsigned long long)e * (unsigned)chunksPerEntry) * ITEMS;
         const int2 wk = work[e];
-        if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, CsNc, false>(A, hcsAll, hcsPrevAll, wk, k0, batches, alpha);
+        if constexpr (VER == 3) nupd += sc_update_unit_v2<Z, 16, CsNc, false>(A, hcsAll, hcsPrevAll, wk, k0, batches, alpha);
+        else if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, 8, CsNc, false>(A, hcsAll, hcsPrevAll, wk, k0, batches, alpha);
         else nupd += sc_update_unit_v1<Z, CsNc, false>(A, hcsAll, hcsPrevAll, wk, k0, alpha);
     }
     // bookkeeping: pairs rewritten, and the last BLOCK out empties the list (one atomic per block: a launch with little work
@@ -934,7 +935,7 @@ __device__ __noinline__ void small_update(const ogn_small_phase &P, int member, 
         const unsigned e = (unsigned)(unit / P.chunks);
         const int c = (int)(unit - (long long)e * P.chunks);
         const int2 wk = __ldcg(work + e);
-        if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, CS, true>(P.u.learn, P.hcs, P.hcsPrev, wk, c * ITEMS, P.updBatches, P.alpha);
+        if constexpr (VER == 2) nupd += sc_update_unit_v2<Z, 8, CS, true>(P.u.learn, P.hcs, P.hcsPrev, wk, c * ITEMS, P.updBatches, P.alpha);
         else nupd += sc_update_unit_v1<Z, CS, true>(P.u.learn, P.hcs, P.hcsPrev, wk, c * ITEMS, P.alpha);
     }
 #pragma unroll
