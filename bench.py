@@ -479,7 +479,9 @@ def main():
     kinds = [args.stream if k in ("noisy", "coherent", "iid") else k for k in cfg["streams"]]
     has_action = "action" in kinds
     n_in = len(cfg["inputSizes"])
-    total = burn + W + K
+    Ke = K
+    total = burn + W + K + Ke  # the end-to-end leg gets its own, fresh window of the stream (re-feeding the timed window would
+    # show the encoder inputs it has just adapted to: fewer weight rewrites, a faster step than the device-resident leg)
     if ens:
         gk = [rank * B + k for k in range(B)]
         host_in = [np.stack([np.concatenate([streams.make(kinds[0], t, cfg["inputSizes"][0], seed=7 + k, shift=17 * k) for k in gk])
@@ -542,7 +544,6 @@ def main():
     value = K / (ms / 1000.0) * (B * world if ens else 1)  # c5: hierarchy steps/s summed over every member on every GPU
 
     # ------------------------------------------------------------------------------------------------ e2e (host API)
-    Ke = K
     barrier()
     pred_idx = [i for i, t in enumerate(cfg["inputTypes"]) if t != InputType.none]
     # streaming callers collect the prediction of step t after queueing step t + 1 (ogn_prediction_readback_queue/finish:
@@ -560,15 +561,23 @@ def main():
         n_out = (cfg["inputSizes"][pi][0] if rx1 <= rx0 else rx1 - rx0) * cfg["inputSizes"][pi][1] * B
         out_buf = np.empty(n_out, dtype=np.int32)
         ticket = None
-        for t in range(burn + W, burn + W + Ke):
+        trace = [] if os.environ.get("OGN_BENCH_E2E_TRACE") == "1" else None
+        for t in range(burn + W + K, burn + W + K + Ke):
+            t_a = time.perf_counter()
             h.step([a[t] for a in host_in], True)
+            t_b = time.perf_counter()
             nxt = h.predictionReadbackQueue(pi, rx0, rx1)
+            t_c = time.perf_counter()
             if ticket is not None:
                 h.predictionReadbackFinish(ticket, out_buf)
             ticket = nxt
+            if trace is not None:
+                trace.append((round((t_b - t_a) * 1e3, 3), round((t_c - t_b) * 1e3, 3), round((time.perf_counter() - t_c) * 1e3, 3)))
         h.predictionReadbackFinish(ticket, out_buf)
+        if trace is not None and rank == 0:
+            print("e2e trace (ms: step, queue, finish):", trace[:12], "...", trace[-4:], file=sys.stderr)
     else:
-        for t in range(burn + W, burn + W + Ke):
+        for t in range(burn + W + K, burn + W + K + Ke):
             h.step([a[t] for a in host_in], True)
             for i in pred_idx:
                 h.getPredictionCs(i)

@@ -1,16 +1,22 @@
-# round 2, call H (1 GPU): update kernel with 64-byte full stores, then the whole GPU suite
 cd /root/repo
-O=gpurun_out/r2h; mkdir -p $O
+O=gpurun_out/r2j; mkdir -p $O
 run() { name=$1; shift; timeout "${T:-300}" "$@" > $O/$name.log 2>&1; echo "$name rc=$?" | tee -a $O/summary.txt; }
-T=300 run t_upd3 env OGN_SC_UPDATE=3 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "c2_video_small or c4_large_layer_small or c5_unit or c1_sine"
-T=300 run t_upd2 env OGN_SC_UPDATE=2 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "c2_video_small or c4_large_layer_small or c5_unit"
-T=300 run u_v1 python bench.py --no-cpu --steps 60 --warmup 5
-T=300 run u_v3 env OGN_SC_UPDATE=3 python bench.py --no-cpu --steps 60 --warmup 5
-T=300 run u_v3b1 env OGN_SC_UPDATE=3 OGN_UPD2_BATCHES=1 python bench.py --no-cpu --steps 60 --warmup 5
-T=300 run u_v2 env OGN_SC_UPDATE=2 python bench.py --no-cpu --steps 60 --warmup 5
-T=1500 run t_all python -m pytest tests -m gpu -q
-tail -n 3 $O/t_*.log
-grep -h '"metric"' $O/u_*.log | python -c "
+T=300 run e2e20 env OGN_BENCH_E2E_TRACE=1 python bench.py --no-cpu --steps 20 --warmup 5
+T=300 run e2e60 env OGN_BENCH_E2E_TRACE=1 python bench.py --no-cpu --steps 60 --warmup 5
+grep -h "e2e trace" $O/*.log
+grep -h '"metric"' $O/e*.log | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(round(d['value'],1), 'e2e', round(d['e2e']['value'],1), d['steps'])
+"
+# small configs with the side stream inside captured graphs
+for w in c1 c2 c5; do
+  T=300 run b_${w}_side env OGN_SIDE_STREAM=1 python bench.py --no-cpu --workload $w
+done
+T=300 run b_c3_side env OGN_SIDE_STREAM=1 python bench.py --no-cpu --workload c3
+T=300 run t_side env OGN_SIDE_STREAM=1 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "c1_sine or c2_video_small or c4_large_layer_small or c5_unit or parameter_changes or learning_disabled or odd"
+tail -n 3 $O/t_side.log
+grep -h '"metric"' $O/b_*.log | python -c "
 import sys, json
 for l in sys.stdin:
     d = json.loads(l); k = d['roofline']['kernels']

@@ -56,11 +56,15 @@ DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
     if (const char *e = std::getenv("OGN_SMALL_MAX_UNITS")) smallMaxUnits = std::atoi(e);
 }
 
+// In a dry run (the step's host code replayed for its state transitions while a captured graph does the work) nothing is
+// queued: the graph holds the fork/join edges that were captured.
 void DeviceContext::forkSide() {
+    if (dry) return;
     cudaCheck(cudaEventRecord(evFork, stream), "cudaEventRecord");
     cudaCheck(cudaStreamWaitEvent(side, evFork, 0), "cudaStreamWaitEvent");
 }
 void DeviceContext::learnQueued() {
+    if (dry) return;
     cudaCheck(cudaEventRecord(evLearn, side), "cudaEventRecord");
     learnPending = true;
 }

@@ -334,7 +334,7 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
             if (!any) { ctx.forkSide(); any = true; }
             pLayers[0][p]->stepDevice(cs, true, m.histories[0][p].slot(0), false, nullptr, false, true);
         }
-        if (any) cudaCheck(cudaEventRecord(ctx.evPredLearn, ctx.side), "cudaEventRecord");
+        if (any && !ctx.dry) cudaCheck(cudaEventRecord(ctx.evPredLearn, ctx.side), "cudaEventRecord");
         predLearnPending = any;
     }
 
@@ -373,7 +373,7 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
             // exchange between shards is deferred to the side stream
             const bool hoisted = l == 0 && hoistPredLearn;
             if (hoisted && predLearnPending) {
-                cudaCheck(cudaStreamWaitEvent(ctx.stream, ctx.evPredLearn, 0), "cudaStreamWaitEvent");
+                if (!ctx.dry) cudaCheck(cudaStreamWaitEvent(ctx.stream, ctx.evPredLearn, 0), "cudaStreamWaitEvent");
                 predLearnPending = false;
             }
             pLayers[l][p]->stepDevice(cs, learnEnabled && !hoisted, target, true, fb, l == 0);
@@ -448,7 +448,9 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
 
     // Graph replay (single device, single stream, no Actor: the Actor uploads fresh host-drawn numbers every step; a
     // profiled step is queued normally so that its kernels can be bracketed by events).
-    bool graphOk = ctx.graphs && !ctx.useSide && cs.shardWorld == 1 && !(ctx.profiling && ctx.sampleThis) && m.graphs.size() < 1024;
+    // With the side stream on one device (SparseCoder learn next to the upper layers' forward passes and the Predictors) the
+    // capture records the fork/join edges, so the graph runs the independent kernels of a step side by side.
+    bool graphOk = ctx.graphs && cs.shardWorld == 1 && !(ctx.profiling && ctx.sampleThis) && m.graphs.size() < 1024;
     for (size_t p = 0; p < aLayers.size() && graphOk; p++)
         if (aLayers[p]) graphOk = false;
     if (!graphOk) { body(); return; }
