@@ -555,11 +555,15 @@ def main():
     if pipelined and world > 1 and not ens:
         X = cfg["inputSizes"][pred_idx[0]][0]
         rx0, rx1 = rank * X // world, (rank + 1) * X // world
-    w0 = time.perf_counter()
     if pipelined:
         pi = pred_idx[0]
         n_out = (cfg["inputSizes"][pi][0] if rx1 <= rx0 else rx1 - rx0) * cfg["inputSizes"][pi][1] * B
         out_buf = np.empty(n_out, dtype=np.int32)
+        for _ in range(2):  # one-time set-up outside the timed region: copy stream, events and the two pinned slots
+            h.predictionReadbackFinish(h.predictionReadbackQueue(pi, rx0, rx1), out_buf)
+        barrier()
+    w0 = time.perf_counter()
+    if pipelined:
         ticket = None
         trace = [] if os.environ.get("OGN_BENCH_E2E_TRACE") == "1" else None
         for t in range(burn + W + K, burn + W + K + Ke):

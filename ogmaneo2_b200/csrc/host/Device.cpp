@@ -49,7 +49,7 @@ DeviceContext::DeviceContext(int dev) : device(dev), stream(nullptr) {
     cudaCheck(cudaEventCreateWithFlags(&evLearn, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evExchange, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evPredLearn, cudaEventDisableTiming), "cudaEventCreate");
-    if (const char *e = std::getenv("OGN_SIDE_STREAM")) useSide = std::atoi(e) != 0; // 0: everything on one stream
+    if (const char *e = std::getenv("OGN_SIDE_STREAM")) { useSide = std::atoi(e) != 0; sideForced = true; } // 0: everything on one stream
     if (const char *e = std::getenv("OGN_GRAPHS")) graphs = std::atoi(e) != 0;
     if (const char *e = std::getenv("OGN_SMALL_KERNEL")) small = std::atoi(e) != 0;
     if (std::getenv("OGN_KERNELS")) small = false; // a forced kernel variant means the per-phase launches are under test

@@ -80,6 +80,7 @@ struct DeviceContext {
     cudaStream_t side;
     cudaEvent_t evFork, evLearn, evExchange, evPredLearn;
     bool learnPending = false, exchangePending = false, useSide = true;
+    bool sideForced = false; // OGN_SIDE_STREAM was given: Hierarchy does not choose
     // graphs: Hierarchy::step may capture its kernel sequence into CUDA graphs (OGN_GRAPHS=0 disables). dry: the step's
     // host code runs for its state transitions only, nothing is queued (the captured graph is launched instead).
     bool graphs = true, dry = false, dryUncounted = false;

@@ -235,6 +235,17 @@ bool Hierarchy::smallEligible(ComputeSystem &cs) {
     DeviceContext &ctx = *m.ctx;
     if (m.smallOk >= 0) return m.smallOk == 1;
     m.smallOk = 0;
+    // Stream choice, once per hierarchy (OGN_SIDE_STREAM overrides): sharded layers always use the side stream (§5); on one
+    // device it pays when the layers are small, where a step is a chain of short latency-bound kernels and SparseCoder
+    // learn can run next to the upper layers' forward passes and the Predictors (measured: C1 +18 %, C2 +23 %, C3 +38 %,
+    // C5 +6 %; captured into the step graphs with its fork/join edges). Large layers keep one stream: their kernels are
+    // bandwidth-bound either way and the hoisted Predictor learn would cost a second pass over the launch overheads.
+    if (!ctx.sideForced && cs.shardWorld == 1 && !ctx.small) {
+        int cols = 0;
+        for (auto &sc : scLayers) cols = std::max(cols, sc.getHiddenSize().x * sc.getHiddenSize().y);
+        for (auto &sz : inputSizes) cols = std::max(cols, sz.x * sz.y);
+        ctx.useSide = cols <= 4096;
+    }
     if (!ctx.small || ctx.useSide || cs.shardWorld != 1 || (int)inputSizes.size() > OGN_SMALL_MAX_INPUTS) return false;
     for (auto &a : aLayers)
         if (a) return false; // the Actor takes fresh host-drawn numbers every step
