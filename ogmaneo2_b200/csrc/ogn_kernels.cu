@@ -21,6 +21,7 @@
 
 #include "../../include/ogn_kernels_api.h"
 #include "ogn_libm.h"
+#include "ogn_stdsort.h"
 
 namespace {
 
@@ -896,12 +897,25 @@ k_ienc_step(const __grid_constant__ ogn_ienc_args A, int Hx, int Hy, int Hz, int
     group_argmax<G>(sm, bv, bi);
     if (hc == 0 && colValid) hiddenCs[col] = bv > -999999.0f ? bi : 0;
     if (!learn) return;
-    // rank of this cell among the column's cells, activations descending, equal ones in cell order (the reference sorts
-    // with a comparator on the value only; a stable order is what its sort produces whenever no two activations tie)
+    // rank of this cell among the column's cells, activations descending. The reference ranks with std::sort and a
+    // comparator on the value only (ImageEncoder.cpp:15-17, :56): without equal activations every sort gives the same
+    // permutation, and up to 16 cells std::sort is a (stable) insertion sort; for a larger column that holds a tie the
+    // group replays libstdc++'s introsort (ogn_stdsort.h) so that tied cells get the ranks the reference gives them.
     int rank = 0;
+    bool tie = false;
     for (int j = 0; j < Hz; ++j) {
         const float sj = __shfl_sync(sm, sum, j, G);
         if (sj > sum || (sj == sum && j < hc)) rank++;
+        tie |= act && j != hc && sj == sum;
+    }
+    if (G == 32 && Hz > 16) {
+        if (__any_sync(sm, tie)) {
+            float key[32];
+            int idx[32];
+            for (int j = 0; j < Hz; ++j) { key[j] = __shfl_sync(sm, sum, j, G); idx[j] = j; }
+            ogn_stdsort::sort_desc(key, idx, Hz);
+            for (int i = 0; i < Hz; ++i) if (idx[i] == hc) rank = i;
+        }
     }
     if (!act) return;
     float *res = resources + col * Hz + hc;

@@ -92,10 +92,10 @@ struct Encoder {
                 }
                 hiddenCs[(size_t)oy + (size_t)ox * Hy] = maxIndex;
                 if (!learn) continue;
-                // the reference calls std::sort with a comparator on the value only ("largest in front"); this restatement uses
-                // a stable sort, which is the same permutation whenever no two activations of a column are equal (and always
-                // for up to 16 cells, where std::sort is an insertion sort)
-                std::stable_sort(act.begin(), act.end(), [](const std::pair<float, int> &a, const std::pair<float, int> &b) { return a.first > b.first; });
+                // the reference calls std::sort with a comparator on the value only ("largest in front"). std::sort is not
+                // stable, so for equal activations the order is whatever libstdc++'s introsort leaves; this restatement makes the
+                // same call (same library, same permutation). The CUDA path replays that algorithm (csrc/ogn_stdsort.h).
+                std::sort(act.begin(), act.end(), [](const std::pair<float, int> &a, const std::pair<float, int> &b) { return a.first > b.first; });
                 for (int i = 0; i < Hz; i++) {
                     const int hc = act[(size_t)i].second;
                     float &res = hiddenResources[(size_t)hc + (size_t)Hz * ((size_t)oy + (size_t)ox * Hy)];
