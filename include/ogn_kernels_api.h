@@ -313,6 +313,8 @@ int ogn_weights_fr_mismatch(const ogn_wset *wset_host, const ogn_rf *rf_host, in
  * reconstruction, 2 Predictor step; c = 0 generic one-cell-per-lane, 1 vec1, 2 vec2, 3 pipe4, 4 pipe6, 5 tma, 6 wide, 7 unused.
  * Tests use it to assert which kernel the default selector ran at a given size. */
 void ogn_debug_variant_launches(long long out[24]);
+/* debug timeline of the tile-staged ImageEncoder kernel: see ogn_kernels.cu */
+int ogn_debug_ienc_trace(int blocks, long long *out);
 
 /* Device replays of glibc expf/tanhf (csrc/ogn_libm.h), exposed for tests: out[i] = f(in[i]). */
 int ogn_test_expf(const float *in, float *out, int64_t n, void *stream);

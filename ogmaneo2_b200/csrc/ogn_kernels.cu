@@ -870,6 +870,31 @@ __device__ __forceinline__ void ienc_hebb(float *w, const float *in, const PackC
         }
 }
 
+// rank of this cell among the column's cells, activations descending. The reference ranks with std::sort and a
+// comparator on the value only (ImageEncoder.cpp:15-17, :56): without equal activations every sort gives the same
+// permutation, and up to 16 cells std::sort is a (stable) insertion sort; for a larger column that holds a tie the
+// group replays libstdc++'s introsort (ogn_stdsort.h) so that tied cells get the ranks the reference gives them.
+template <int G>
+__device__ __forceinline__ int ienc_rank(unsigned sm, float sum, int hc, int Hz, bool act) {
+    int rank = 0;
+    bool tie = false;
+    for (int j = 0; j < Hz; ++j) {
+        const float sj = __shfl_sync(sm, sum, j, G);
+        if (sj > sum || (sj == sum && j < hc)) rank++;
+        tie |= act && j != hc && sj == sum;
+    }
+    if (G == 32 && Hz > 16) {
+        if (__any_sync(sm, tie)) {
+            float key[32];
+            int idx[32];
+            for (int j = 0; j < Hz; ++j) { key[j] = __shfl_sync(sm, sum, j, G); idx[j] = j; }
+            ogn_stdsort::sort_desc(key, idx, Hz);
+            for (int i = 0; i < Hz; ++i) if (idx[i] == hc) rank = i;
+        }
+    }
+    return rank;
+}
+
 template <int G>
 __global__ void __launch_bounds__(kThreads)
 k_ienc_step(const __grid_constant__ ogn_ienc_args A, int Hx, int Hy, int Hz, int npacks, int packsPerRow, int learn, float alpha, float gamma,
@@ -897,26 +922,7 @@ k_ienc_step(const __grid_constant__ ogn_ienc_args A, int Hx, int Hy, int Hz, int
     group_argmax<G>(sm, bv, bi);
     if (hc == 0 && colValid) hiddenCs[col] = bv > -999999.0f ? bi : 0;
     if (!learn) return;
-    // rank of this cell among the column's cells, activations descending. The reference ranks with std::sort and a
-    // comparator on the value only (ImageEncoder.cpp:15-17, :56): without equal activations every sort gives the same
-    // permutation, and up to 16 cells std::sort is a (stable) insertion sort; for a larger column that holds a tie the
-    // group replays libstdc++'s introsort (ogn_stdsort.h) so that tied cells get the ranks the reference gives them.
-    int rank = 0;
-    bool tie = false;
-    for (int j = 0; j < Hz; ++j) {
-        const float sj = __shfl_sync(sm, sum, j, G);
-        if (sj > sum || (sj == sum && j < hc)) rank++;
-        tie |= act && j != hc && sj == sum;
-    }
-    if (G == 32 && Hz > 16) {
-        if (__any_sync(sm, tie)) {
-            float key[32];
-            int idx[32];
-            for (int j = 0; j < Hz; ++j) { key[j] = __shfl_sync(sm, sum, j, G); idx[j] = j; }
-            ogn_stdsort::sort_desc(key, idx, Hz);
-            for (int i = 0; i < Hz; ++i) if (idx[i] == hc) rank = i;
-        }
-    }
+    const int rank = ienc_rank<G>(sm, sum, hc, Hz, act);
     if (!act) return;
     float *res = resources + col * Hz + hc;
     const float r = *res;
@@ -952,6 +958,175 @@ k_ienc_reconstruct(const __grid_constant__ ogn_ienc_args A, int vli, int Hy, int
 }
 
 #include "ogn_vec.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+// ImageEncoder step with the pack's weight block staged in shared memory. In the F layout the weights of one column pack
+// are ONE contiguous block (union slots x Vz rows of P*Hz floats; 31 KB for a radius-4 RGB field), every slot of which the
+// dense distance reads: one warp owns one pack, an elected lane pulls the block(s) in with cp.async.bulk (completion on an
+// mbarrier) while the warp stages the dense input patch, the distance / arg-max / ranking run out of shared memory, the
+// Hebbian pass updates the block in place and one bulk store writes it back. DRAM sees every weight once in and once out
+// (8 B per weight and learning step instead of the 12 B of the two-pass kernel above), and with ~7 packs resident per SM
+// there are >200 KB of copies in flight per SM without any register cost. Sums run in the reference's order (visible layer,
+// slot x-major, y, visible cell), so results are bit-identical to k_ienc_step.
+struct IencTileLayout { int wOff[OGN_MAX_IENC_VL], inOff[OGN_MAX_IENC_VL], barOff; }; // float offsets into the warp's smem
+
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(vec::smem_u32(src)), "r"(bytes) : "memory");
+}
+
+// n consecutive rows of the staged block (this lane's float of every row, rows RW floats apart) against the staged patch:
+// eight rows of loads in flight before the first add, adds in row order (the reference's order). RW32: the row is one
+// 128-byte line (every power-of-two Hz), which turns the row stride into immediate offsets.
+template <bool RW32>
+__device__ __forceinline__ float ienc_rows_d2(const float *__restrict__ wp, const float *__restrict__ sp, int n, int rowW, float d2) {
+    const int RW = RW32 ? 32 : rowW;
+    for (; n >= 8; n -= 8, wp += 8 * RW, sp += 8) {
+        float wv[8], iv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { wv[k] = wp[k * RW]; iv[k] = sp[k]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = iv[k] - wv[k]; d2 += d * d; }
+    }
+    for (; n > 0; --n, wp += RW, ++sp) { const float d = *sp - *wp; d2 += d * d; }
+    return d2;
+}
+template <bool RW32>
+__device__ __forceinline__ void ienc_rows_hebb(float *__restrict__ wp, const float *__restrict__ sp, int n, int rowW, float strength) {
+    const int RW = RW32 ? 32 : rowW;
+    for (; n >= 8; n -= 8, wp += 8 * RW, sp += 8) {
+        float wv[8], iv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { wv[k] = wp[k * RW]; iv[k] = sp[k]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wp[k * RW] = wv[k] + strength * (iv[k] - wv[k]);
+    }
+    for (; n > 0; --n, wp += RW, ++sp) { const float old = *wp; *wp = old + strength * (*sp - old); }
+}
+
+template <int G, bool RW32>
+__global__ void __launch_bounds__(32)
+k_ienc_step_t(const __grid_constant__ ogn_ienc_args A, const __grid_constant__ IencTileLayout L, int Hx, int Hy, int Hz, int packsPerRow,
+              int learn, float alpha, float gamma, float *resources, int *__restrict__ hiddenCs, long long *trace, int traceBlocks) {
+    constexpr int P = Pack<G>::P;
+    // debug timeline (ogn_debug_ienc_trace): lane 0 of the first traceBlocks blocks stamps clock64() at every stage
+#define IENC_STAMP(i) do { if (trace && threadIdx.x == 0 && (int)blockIdx.x < traceBlocks) trace[(long long)blockIdx.x * 12 + (i)] = clock64(); } while (0)
+    if (trace && threadIdx.x == 0 && (int)blockIdx.x < traceBlocks) {
+        unsigned smid; unsigned long long gt;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        trace[(long long)blockIdx.x * 12 + 10] = smid; trace[(long long)blockIdx.x * 12 + 11] = (long long)gt;
+    }
+    IENC_STAMP(0);
+    float *sm = reinterpret_cast<float *>(vec::ogn_dyn_smem);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + L.barOff); // one per visible layer
+    const int gl = threadIdx.x;
+    const int pack = blockIdx.x;
+    const unsigned gm = lane_mask<G>();
+    const int ox = pack / packsPerRow, q = pack % packsPerRow;
+    const int p = gl / G, hc = gl % G;
+    const int oy = q * P + p;
+    const bool colValid = oy < Hy, act = colValid && hc < Hz;
+    const long long col = (long long)ox * Hy + (colValid ? oy : Hy - 1);
+    const int rowW = P * Hz;
+    const int li = p * Hz + (hc < Hz ? hc : Hz - 1);
+
+    if (gl == 0) {
+        for (int v = 0; v < A.nvl; ++v) vec::mbar_init_nofence(bars + v);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int v = 0; v < A.nvl; ++v) {
+            const ogn_rf &rf = A.geo[A.vl[v].geo];
+            const unsigned tb = (unsigned)(__ldg(rf.nx + ox) * __ldg(rf.nyf + q) * rf.Vz * rowW) * 4u;
+            vec::mbar_expect_tx(bars + v, tb);
+            if (tb) vec::bulk_g2s(sm + L.wOff[v], A.vl[v].wf + f_block(rf, ox, q), tb, bars + v);
+        }
+    }
+    IENC_STAMP(1);
+    // this cell's resource, needed after the ranking: start the load now
+    float resv = 0.0f;
+    if (learn && act) resv = resources[col * Hz + hc];
+    // dense input patch of the union field (a row of the patch is contiguous in the input: y-major, cell-minor)
+    for (int v = 0; v < A.nvl; ++v) {
+        const ogn_rf &rf = A.geo[A.vl[v].geo];
+        const int lx = __ldg(rf.lox + ox), nxv = __ldg(rf.nx + ox), lyU = __ldg(rf.loyf + q), nyU = __ldg(rf.nyf + q);
+        const int rowF = nyU * rf.Vz, n = nxv * rowF;
+        float *si = sm + L.inOff[v];
+        const float *base = A.vl[v].in + (long long)rf.Vz * (lyU + (long long)rf.Vy * lx);
+        for (int i0 = 0; i0 < n; i0 += 32 * 8) { // eight independent loads per lane before the first store
+            float t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = min(i0 + k * 32 + gl, n - 1);
+                t[k] = __ldg(base + (long long)(i / rowF) * rf.Vy * rf.Vz + i % rowF);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (i0 + k * 32 + gl < n) si[i0 + k * 32 + gl] = t[k];
+        }
+    }
+    __syncwarp(); // barriers initialised, patch visible to the warp
+    IENC_STAMP(2);
+
+    float sum = 0.0f;
+    for (int v = 0; v < A.nvl; ++v) {
+        const ogn_rf &rf = A.geo[A.vl[v].geo];
+        const PackCtx c = pack_ctx(rf, ox, q, p);
+        const float *w = sm + L.wOff[v] + li, *si = sm + L.inOff[v];
+        vec::mbar_wait(bars + v, 0);
+        if (v == 0) IENC_STAMP(3);
+        float d2 = 0.0f;
+        if (P == 1) // the union field is the column's field: all rows, front to back
+            d2 = ienc_rows_d2<RW32>(w, si, c.nslotsU * rf.Vz, rowW, d2);
+        else {      // the column's own rows of every visible x are contiguous
+            const int nxv = c.nyU > 0 ? c.nslotsU / c.nyU : 0;
+            for (int dx = 0; dx < nxv; ++dx) {
+                const int r0 = (dx * c.nyU + c.dlo) * rf.Vz;
+                d2 = ienc_rows_d2<RW32>(w + (long long)r0 * rowW, si + r0, c.dn * rf.Vz, rowW, d2);
+            }
+        }
+        sum -= act ? d2 : 0.0f;
+    }
+    IENC_STAMP(4);
+    float bv = (act && sum > -999999.0f) ? sum : (act ? -999999.0f : -INFINITY);
+    int bi = act ? hc : 0x7fffffff;
+    group_argmax<G>(gm, bv, bi);
+    if (hc == 0 && colValid) hiddenCs[col] = bv > -999999.0f ? bi : 0;
+    if (!learn) return;
+    const int rank = ienc_rank<G>(gm, sum, hc, Hz, act);
+    float strength = 0.0f;
+    if (act) {
+        strength = ogn_expf((float)(-rank * rank) * gamma / fmaxf(0.001f, resv)) * resv;
+        resources[col * Hz + hc] = resv - alpha * strength;
+    }
+    IENC_STAMP(5);
+    for (int v = 0; v < A.nvl; ++v) {
+        const ogn_rf &rf = A.geo[A.vl[v].geo];
+        const PackCtx c = pack_ctx(rf, ox, q, p);
+        float *w = sm + L.wOff[v] + li;
+        const float *si = sm + L.inOff[v];
+        if (act) {
+            if (P == 1)
+                ienc_rows_hebb<RW32>(w, si, c.nslotsU * rf.Vz, rowW, strength);
+            else {
+                const int nxv = c.nyU > 0 ? c.nslotsU / c.nyU : 0;
+                for (int dx = 0; dx < nxv; ++dx) {
+                    const int r0 = (dx * c.nyU + c.dlo) * rf.Vz;
+                    ienc_rows_hebb<RW32>(w + (long long)r0 * rowW, si + r0, c.dn * rf.Vz, rowW, strength);
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // this lane's generic-proxy writes before the bulk store reads them
+        __syncwarp();
+        const unsigned tb = (unsigned)(c.nslotsU * rf.Vz * rowW) * 4u;
+        if (gl == 0 && tb) bulk_s2g(A.vl[v].wf + c.blk, sm + L.wOff[v], tb);
+    }
+    IENC_STAMP(6);
+    if (gl == 0) {
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the stores' reads
+    }
+    IENC_STAMP(7);
+#undef IENC_STAMP
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Weight (re)layout, init and checks. One block per hidden column; threads walk the column's CSR-order elements
@@ -1211,6 +1386,8 @@ static int vec_threads(int variant) { // threads per block of the 128-bit kernel
 // cp.async ring variants of round 1), 5 tma, 6 wide, 7 wide2) since the library was loaded: lets a test assert which kernel
 // a size actually ran (ogn_debug_variant_launches)
 static long long g_variantLaunches[3][8];
+static long long *g_iencTrace = nullptr; // ogn_debug_ienc_trace
+static int g_iencTraceBlocks = 0;
 static void count_variant(int kernel, int variant) {
     const int col = variant == kVarScalar ? 0 : variant == kVarVec1 ? 1 : variant == kVarVec2 ? 2 : variant == kVarTma ? 5 : variant == kVarWide ? 6 : 7;
     g_variantLaunches[kernel][col]++;
@@ -1441,6 +1618,38 @@ int ogn_image_encoder_step(const ogn_ienc_args *args, int Hx, int Hy, int Hz, in
     for (int v = 0; v < args->nvl; v++)
         if (args->geo[args->vl[v].geo].pf != P) return (int)cudaErrorInvalidValue;
     if (npacks <= 0) return 0;
+    // tile-staged kernel when the largest pack's blocks and input patches fit the shared memory of an SM (OGN_IENC_TILE=0: never)
+    static const int useTile = env_int("OGN_IENC_TILE", 1);
+    IencTileLayout L;
+    int floats = 0;
+    for (int v = 0; v < args->nvl; v++) {
+        const ogn_rf &rf = args->geo[args->vl[v].geo];
+        L.wOff[v] = floats;
+        floats += rf.max_nx * rf.max_nyf * rf.Vz * P * Hz; // multiple of 4 floats when P * Hz is; checked below
+    }
+    for (int v = 0; v < args->nvl; v++) {
+        const ogn_rf &rf = args->geo[args->vl[v].geo];
+        L.inOff[v] = floats;
+        floats += (rf.max_nx * rf.max_nyf * rf.Vz + 3) & ~3;
+    }
+    L.barOff = floats;
+    const size_t smem = (size_t)floats * 4 + 8 * (size_t)OGN_MAX_IENC_VL;
+    if (useTile && (P * Hz) % 4 == 0 && smem <= 200 * 1024) {
+        bool ok = true;
+        const cudaStream_t st = (cudaStream_t)stream;
+        if (P * Hz == 32) {
+            OGN_DISPATCH_G(g, (ok = cudaFuncSetAttribute(k_ienc_step_t<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess));
+            if (!ok) return (int)cudaGetLastError();
+            OGN_DISPATCH_G(g, (k_ienc_step_t<G, true><<<(unsigned)npacks, 32, smem, st>>>(*args, L, Hx, Hy, Hz, ppr, learn, alpha, gamma, resources,
+                                                                                        hidden_cs, g_iencTrace, g_iencTraceBlocks)));
+        } else {
+            OGN_DISPATCH_G(g, (ok = cudaFuncSetAttribute(k_ienc_step_t<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess));
+            if (!ok) return (int)cudaGetLastError();
+            OGN_DISPATCH_G(g, (k_ienc_step_t<G, false><<<(unsigned)npacks, 32, smem, st>>>(*args, L, Hx, Hy, Hz, ppr, learn, alpha, gamma, resources,
+                                                                                         hidden_cs, g_iencTrace, g_iencTraceBlocks)));
+        }
+        return launch_status();
+    }
     dim3 grid((unsigned)(((long long)npacks * g * P + kThreads - 1) / kThreads));
     OGN_DISPATCH_G(g, (k_ienc_step<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*args, Hx, Hy, Hz, npacks, ppr, learn, alpha, gamma, resources,
                                                                                 hidden_cs)));
@@ -1575,6 +1784,28 @@ int ogn_weights_fr_mismatch(const ogn_wset *ws, const ogn_rf *rf, int member, un
                                                                         ws->wr + (long long)member * ws->wr_mstride, ws->wr_base,
                                                                         xa * rf->Hy, count_dev);
     return launch_status();
+}
+
+// Timeline of the tile-staged ImageEncoder kernel: (blocks, NULL) arms a device buffer of 12 words per block (stamps 0..7 =
+// clock64 at start / copies queued / patch staged / block landed / distances done / ranked / updated / stored, 10 = SM id,
+// 11 = globaltimer at start); (blocks, out) copies it to the host and disarms. Returns 0 or a CUDA error.
+int ogn_debug_ienc_trace(int blocks, long long *out) {
+    if (!out) {
+        if (g_iencTrace) cudaFree(g_iencTrace);
+        g_iencTrace = nullptr; g_iencTraceBlocks = 0;
+        if (blocks <= 0) return 0;
+        cudaError_t e = cudaMalloc(&g_iencTrace, (size_t)blocks * 12 * sizeof(long long));
+        if (e != cudaSuccess) return (int)e;
+        cudaMemset(g_iencTrace, 0, (size_t)blocks * 12 * sizeof(long long));
+        g_iencTraceBlocks = blocks;
+        return 0;
+    }
+    if (!g_iencTrace) return (int)cudaErrorInvalidValue;
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaMemcpy(out, g_iencTrace, (size_t)(blocks < g_iencTraceBlocks ? blocks : g_iencTraceBlocks) * 12 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(g_iencTrace);
+    g_iencTrace = nullptr; g_iencTraceBlocks = 0;
+    return (int)e;
 }
 
 void ogn_debug_variant_launches(long long out[24]) { memcpy(out, g_variantLaunches, sizeof(g_variantLaunches)); }

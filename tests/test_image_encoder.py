@@ -16,6 +16,7 @@ CASES = {
     "two_layers": dict(hidden=(5, 5, 8), visible=[((5, 5, 4), 1), ((9, 7, 2), 3)]),  # two inputs, clamped fields
     "z32": dict(hidden=(4, 6, 32), visible=[((8, 6, 1), 2)]),                        # 32 cells per column (std::sort past its insertion-sort size)
     "odd": dict(hidden=(3, 4, 5), visible=[((7, 3, 2), 1)]),                         # Z off the powers of two
+    "z18": dict(hidden=(3, 3, 18), visible=[((6, 6, 2), 2)]),                        # row of 18 floats: not bulk-copyable, two-pass kernel
 }
 
 
@@ -131,6 +132,7 @@ TIE_CASES = {
     "z32": dict(hidden=(4, 6, 32), visible=[((8, 6, 1), 2)]),
     "z24_two": dict(hidden=(5, 4, 24), visible=[((5, 4, 2), 1), ((10, 8, 1), 2)]),
     "z16": dict(hidden=(4, 4, 16), visible=[((8, 8, 1), 2)]),  # insertion-sort size: the stable order is the reference's
+    "z18": dict(hidden=(3, 3, 18), visible=[((6, 6, 2), 2)]),  # introsort size on the two-pass kernel (rows not bulk-copyable)
 }
 
 
