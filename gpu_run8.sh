@@ -8,11 +8,9 @@ T=200 run c4_n8_s20 $TR --nproc-per-node 8 --master-port 29512 bench.py --gpus 8
 T=200 run c4_n4_s20 $TR --nproc-per-node 4 --master-port 29513 bench.py --gpus 4 --steps 20 --warmup 5
 T=200 run c4_n2_s20 $TR --nproc-per-node 2 --master-port 29514 bench.py --gpus 2 --steps 20 --warmup 5
 T=300 run c5_n8 $TR --nproc-per-node 8 --master-port 29516 bench.py --gpus 8 --workload c5
-T=200 run ref_n8 $TR --nproc-per-node 8 --master-port 29517 bench.py --impl reference --gpus 8 --steps 20 --warmup 5
 grep -h '"metric"' $O/c*.log | python -c "
 import sys, json
 for l in sys.stdin:
     d = json.loads(l)
     print(d['config']['workload'][:10], d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), d['state_hash']['crc32'], d['steps'], d['warmup'])
 "
-tail -c 600 $O/ref_n8.log

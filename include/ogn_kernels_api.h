@@ -265,7 +265,7 @@ typedef struct ogn_ienc_args {
 } ogn_ienc_args;
 /* ImageEncoder::forward for every hidden column (ImageEncoder.cpp:19-74): activation = -sum of squared distances
  * (SparseMatrix::distance2 :122-137), first-max arg-max -> hidden_cs; with learn != 0 the cells of a column are ranked by
- * activation (descending, stable), strength = expf(-rank^2 * gamma / max(0.001, resource)) * resource, resource -= alpha *
+ * activation (descending; equal activations in the order libstdc++'s std::sort leaves, ogn_stdsort.h), strength = expf(-rank^2 * gamma / max(0.001, resource)) * resource, resource -= alpha *
  * strength, and every weight of the cell moves towards its input by strength (SparseMatrix::hebb :692-701). Hz <= 32. */
 int ogn_image_encoder_step(const ogn_ienc_args *args_host, int Hx, int Hy, int Hz, int learn, float alpha, float gamma, float *resources,
                   int *hidden_cs, void *stream);
