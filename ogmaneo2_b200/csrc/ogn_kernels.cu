@@ -1337,6 +1337,7 @@ static inline bool vec_geo(const ogn_rf &g) {
 // (bandwidth-bound) take vec1, small launches (latency-bound, at most kSmallLaunchPacks packs x members) take the
 // variant OGN_SMALL_VARIANT names (default below), see profiles/README.md.
 constexpr int kVarScalar = 0, kVarVec1 = 1, kVarVec2 = 2, kVarTma = 7, kVarWide = 8, kVarWide2 = 10, kAutoVariant = 9;
+constexpr int kVarStage = 11; // Predictor only: weight rows staged in shared memory by cp.async (the other kernels run vec1)
 constexpr long long kSmallLaunchPacks = 8192; // packs x members at or below which a launch counts as latency-bound
 static int parse_variant(const char *e, int dflt) {
     if (!e) return dflt;
@@ -1346,6 +1347,7 @@ static int parse_variant(const char *e, int dflt) {
     if (!strcmp(e, "tma")) return kVarTma;
     if (!strcmp(e, "wide")) return kVarWide;
     if (!strcmp(e, "wide2")) return kVarWide2;
+    if (!strcmp(e, "stage")) return kVarStage;
     return dflt;
 }
 static int kernel_variant() {
@@ -1389,7 +1391,7 @@ static long long g_variantLaunches[3][8];
 static long long *g_iencTrace = nullptr; // ogn_debug_ienc_trace
 static int g_iencTraceBlocks = 0;
 static void count_variant(int kernel, int variant) {
-    const int col = variant == kVarScalar ? 0 : variant == kVarVec1 ? 1 : variant == kVarVec2 ? 2 : variant == kVarTma ? 5 : variant == kVarWide ? 6 : 7;
+    const int col = variant == kVarScalar ? 0 : variant == kVarVec1 ? 1 : variant == kVarVec2 ? 2 : variant == kVarStage ? 3 : variant == kVarTma ? 5 : variant == kVarWide ? 6 : 7;
     g_variantLaunches[kernel][col]++;
 }
 
@@ -1478,6 +1480,7 @@ int ogn_sc_forward(const ogn_fwd_args *args, int Hx, int Hy, int Hz, int x0, int
     cudaStream_t st = (cudaStream_t)stream;
     if (vecOk) {
         int var = resolve_variant((long long)npacks * batch);
+        if (var == kVarStage) var = kVarVec1; // only the Predictor has the staged-rows variant
         const int vt = vec_threads(var);
         if (var == kVarTma) { // staged CSDR windows: every visible layer must be eligible, else plain vec1
             int ti = 0;
@@ -1524,7 +1527,7 @@ int ogn_sc_learn(const ogn_learn_args *args, const int *hidden_cs, const int *hi
     if (ogn_sc_learn_is_split(args)) {
         const int Vz = args->geo.Vz;
         int var = resolve_variant((long long)npacks * batch * args->nvl);
-        if (var == kVarTma) var = kVarVec1; // the reconstruction has no staged variant
+        if (var == kVarTma || var == kVarStage) var = kVarVec1; // the reconstruction has no staged variant
         const int vt = vec_threads(var);
         const int lanes = is_wide(var) ? 32 : 8;
         dim3 grid((unsigned)(((long long)npacks * lanes + vt - 1) / vt), (unsigned)batch, (unsigned)args->nvl);
@@ -1596,6 +1599,16 @@ int ogn_pred_step(const ogn_pred_args *args, int Hx, int Hy, int Hz, int x0, int
                 return launch_status();
             }
             var = kVarVec1;
+        }
+        if (var == kVarStage) {
+            static const int ns = env_int("OGN_STAGE_CHUNKS", 3); // 8 * ns rows per lane and round: 1..3
+            count_variant(2, kVarStage);
+            dim3 grid((unsigned)(((long long)npacks * 8 + vt - 1) / vt), (unsigned)batch);
+            const size_t smem = (size_t)vt * 8 * (ns >= 3 ? 3 : ns == 2 ? 2 : 1) * sizeof(float4);
+            if (ns >= 3) { OGN_DISPATCH_Z(Hz, (launch_k(vec::k_pred_step_a<Z, 3>, grid, vt, smem, st, *args, Hx, Hy, x0, npacks, ppr, learn, activate, target_cs, alpha, activations, hidden_cs))); }
+            else if (ns == 2) { OGN_DISPATCH_Z(Hz, (launch_k(vec::k_pred_step_a<Z, 2>, grid, vt, smem, st, *args, Hx, Hy, x0, npacks, ppr, learn, activate, target_cs, alpha, activations, hidden_cs))); }
+            else { OGN_DISPATCH_Z(Hz, (launch_k(vec::k_pred_step_a<Z, 1>, grid, vt, smem, st, *args, Hx, Hy, x0, npacks, ppr, learn, activate, target_cs, alpha, activations, hidden_cs))); }
+            return launch_status();
         }
         count_variant(2, var);
         const int lanes = is_wide(var) ? 32 : 8;

@@ -177,6 +177,87 @@ __device__ __forceinline__ void add_delta(unsigned om, int sub, int oct, float *
     }
 }
 
+// ---- rows staged in shared memory (octet mapping) ----------------------------------------------------------------------
+// The same walks as gather<., NS, 8> / add_delta<NS, 8>, but the 8 * NS row pieces a lane has in flight are 16-byte cp.async
+// copies into the lane's own column of a shared-memory stage (stage[r * blockDim.x] for r < 8 * NS) instead of registers:
+// rows in flight cost shared memory, so one round can hold 24 rows per lane (96 KB per block of 256, two blocks per SM)
+// where the register version holds 8. tools/microbench_patterns.cu: for this access pattern (one 128-byte row out of Vz per
+// slot) 27 staged rows per lane reach 5.39 TB/s read-modify-write + gather at two blocks per SM, 9 rows in registers 3.99.
+// A lane only ever reads the pieces it copied itself, so cp.async.wait_group is the only synchronisation needed.
+__device__ __forceinline__ void cp_async16(float4 *dst, const float *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int NS, class CS>
+__device__ __forceinline__ float4 gather_staged(unsigned om, int sub, const float *wl, const int *cs, int rs, const PackCtx &c, int Vz, float4 *stage) {
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (c.nslotsU <= 0) return acc;
+    const int stride = blockDim.x;
+    SlotWalker<CS, 8> sw;
+    sw.init(cs, rs, c, Vz, sub);
+    for (int ch = 0; ch < c.nslotsU; ch += 8 * NS) {
+        unsigned d[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) d[k] = sw.next();
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned dj = __shfl_sync(om, d[k], j, 8);
+                cp_async16(stage + (k * 8 + j) * stride, wl + ((size_t)(dj & kLineMask) << 5));
+            }
+        cp_async_wait_all();
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned dj = __shfl_sync(om, d[k], j, 8);
+                if ((unsigned)((int)(dj >> kLineBits) - c.dlo) < (unsigned)c.dn) {
+                    const float4 w = stage[(k * 8 + j) * stride];
+                    acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+                }
+            }
+    }
+    return acc;
+}
+
+template <int NS, class CS>
+__device__ __forceinline__ void add_delta_staged(unsigned om, int sub, float *wl, const int *cs, int rs, const float4 &delta, const PackCtx &c, int Vz,
+                                                 float4 *stage) {
+    if (c.nslotsU <= 0) return;
+    const int stride = blockDim.x;
+    SlotWalker<CS, 8> sw;
+    sw.init(cs, rs, c, Vz, sub);
+    for (int ch = 0; ch < c.nslotsU; ch += 8 * NS) {
+        unsigned d[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) d[k] = sw.next();
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned dj = __shfl_sync(om, d[k], j, 8);
+                cp_async16(stage + (k * 8 + j) * stride, wl + ((size_t)(dj & kLineMask) << 5));
+            }
+        cp_async_wait_all();
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned dj = __shfl_sync(om, d[k], j, 8);
+                if ((unsigned)((int)(dj >> kLineBits) - c.dlo) < (unsigned)c.dn) {
+                    float4 v = stage[(k * 8 + j) * stride];
+                    v.x += delta.x; v.y += delta.y; v.z += delta.z; v.w += delta.w;
+                    st_plain(wl + ((size_t)(dj & kLineMask) << 5), v);
+                }
+            }
+    }
+}
+
 // First-max arg-max of the reference's forward scans (`if (sum > max)` from (0, -999999), SparseCoder.cpp:31-38,
 // Predictor.cpp:36-43) over the Z cells of a column spread over LC = Z/4 lanes x 4 cells. NaN never wins.
 template <int Z>
@@ -271,10 +352,10 @@ __device__ __forceinline__ void sc_forward_pack(const ogn_fwd_args &A, int Hx, i
 
 // K6+K7 for one pack: Predictor::learn (Predictor.cpp:49-70) then Predictor::forward (:13-47), Hz = Z in {8, 16, 32}.
 // tiles (optional): [v] = staged view of vl[v].cs, [OGN_MAX_PRED_VL + v] = staged view of vl[v].cs_prev.
-template <int Z, int NCH, int W, class CS>
+template <int Z, int NCH, int W, class CS, int STG = 0>
 __device__ __forceinline__ void pred_step_pack(const ogn_pred_args &A, int Hx, int Hy, int x0, int pack, int packsPerRow, int member, int learn,
                                                int activate, const int *target, float alpha, float *acts, int *hiddenCs,
-                                               const CsView *tiles) {
+                                               const CsView *tiles, float4 *stage = nullptr) {
     const int sub = threadIdx.x & 7, oct = (threadIdx.x >> 3) & 3;
     const unsigned om = octet_mask();
     const PackId id = pack_id<Z>(pack, packsPerRow, x0, Hy, sub);
@@ -298,7 +379,8 @@ __device__ __forceinline__ void pred_step_pack(const ogn_pred_args &A, int Hx, i
             CsView cv;
             if (tiles) cv = tiles[OGN_MAX_PRED_VL + v];
             else { cv.p = vl.cs_prev + (long long)member * rf.Vx * rf.Vy; cv.rs = rf.Vy; }
-            add_delta<NCH, W, CS>(om, sub, oct, wl, cv.p, cv.rs, delta, c, rf.Vz);
+            if constexpr (STG > 0) add_delta_staged<STG, CS>(om, sub, wl, cv.p, cv.rs, delta, c, rf.Vz, stage);
+            else add_delta<NCH, W, CS>(om, sub, oct, wl, cv.p, cv.rs, delta, c, rf.Vz);
         }
         if (W == 32) __syncwarp(); // the activate pass re-reads lines another octet of this warp just stored
     }
@@ -314,7 +396,9 @@ __device__ __forceinline__ void pred_step_pack(const ogn_pred_args &A, int Hx, i
         CsView cv;
         if (tiles) cv = tiles[v];
         else { cv.p = vl.cs + (long long)member * rf.Vx * rf.Vy; cv.rs = rf.Vy; }
-        const float4 g = gather<false, NCH, W, CS>(om, sub, oct, wl, cv.p, cv.rs, c, rf.Vz);
+        float4 g;
+        if constexpr (STG > 0) g = gather_staged<STG, CS>(om, sub, wl, cv.p, cv.rs, c, rf.Vz, stage);
+        else g = gather<false, NCH, W, CS>(om, sub, oct, wl, cv.p, cv.rs, c, rf.Vz);
         sum.x += g.x; sum.y += g.y; sum.z += g.z; sum.w += g.w;
         count += c.dn * (c.nslotsU / max(c.nyU, 1)); // own field: nx * ny
     }
@@ -752,6 +836,20 @@ k_pred_step_v(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int x0, i
     const int pack = (blockIdx.x * blockDim.x + threadIdx.x) / W;
     if (pack >= npacks) return;
     pred_step_pack<Z, NCH, W, CsNc>(A, Hx, Hy, x0, pack, packsPerRow, member, learn, activate, target, alpha, acts, hiddenCs, nullptr);
+}
+
+// Predictor step with the weight rows staged in shared memory (8 * NS rows per lane and round; dynamic shared memory =
+// blockDim.x * 8 * NS * 16 bytes)
+template <int Z, int NS>
+__global__ void __launch_bounds__(kThreads)
+k_pred_step_a(const __grid_constant__ ogn_pred_args A, int Hx, int Hy, int x0, int npacks, int packsPerRow, int learn, int activate,
+              const int *__restrict__ target, float alpha, float *acts, int *__restrict__ hiddenCs) {
+    const int member = blockIdx.y;
+    if (activate == 1) pred_copy_inputs<CsNc>(A, member, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    const int pack = (blockIdx.x * blockDim.x + threadIdx.x) / 8;
+    if (pack >= npacks) return;
+    float4 *stage = reinterpret_cast<float4 *>(ogn_dyn_smem) + threadIdx.x;
+    pred_step_pack<Z, 1, 8, CsNc, NS>(A, Hx, Hy, x0, pack, packsPerRow, member, learn, activate, target, alpha, acts, hiddenCs, nullptr, stage);
 }
 
 template <int Z, int NCH, int W>

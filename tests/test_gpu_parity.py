@@ -150,12 +150,12 @@ def test_actor_more_history_samples_than_one_launch_holds(product, oracle):
 
 @pytest.mark.parametrize("env", [
     {"OGN_KERNELS": "scalar"}, {"OGN_KERNELS": "vec1"}, {"OGN_KERNELS": "vec2"}, {"OGN_KERNELS": "tma"}, {"OGN_KERNELS": "wide"},
-    {"OGN_KERNELS": "wide2"}, {"OGN_KERNELS": "vec1", "OGN_SC_UPDATE": "2"}, {"OGN_SC_UPDATE": "2", "OGN_UPD2_BATCHES": "1"},
+    {"OGN_KERNELS": "wide2"}, {"OGN_KERNELS": "stage"}, {"OGN_KERNELS": "stage", "OGN_STAGE_CHUNKS": "1"}, {"OGN_KERNELS": "vec1", "OGN_SC_UPDATE": "2"}, {"OGN_SC_UPDATE": "2", "OGN_UPD2_BATCHES": "1"},
     {"OGN_SMALL_KERNEL": "1"}, {"OGN_SMALL_KERNEL": "1", "OGN_SC_UPDATE": "2"}, {"OGN_GRAPHS": "0"}, {"OGN_SIDE_STREAM": "0"}, {"OGN_SIDE_STREAM": "1", "OGN_GRAPHS": "0"},
 ], ids=lambda e: "-".join(f"{k[4:].lower()}={v}" for k, v in e.items()))
 def test_every_kernel_variant_and_scheduling_mode_is_bit_exact(env):
     """The alternative kernels (generic one-cell-per-lane, deeper register batches, TMA-staged CSDR windows, one warp per
-    pack, the full-sector update kernel) and scheduling modes (the single-launch small-hierarchy step instead of per-phase
+    pack, Predictor weight rows staged in shared memory, the full-sector update kernel) and scheduling modes (the single-launch small-hierarchy step instead of per-phase
     launches, no CUDA graphs, one stream instead of two) are selected per process: rerun a parity subset in a subprocess for
     each. The default run of this file covers per-phase launches captured into graphs with the side stream (small
     hierarchies), `wide` for small launches, `vec1` for large ones and update v1."""
