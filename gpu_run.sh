@@ -1,17 +1,17 @@
 cd /root/repo
-O=gpurun_out/r3a; mkdir -p $O
+O=gpurun_out/r3b; mkdir -p $O
 run() { name=$1; shift; timeout "${T:-300}" "$@" > $O/$name.log 2>&1; echo "$name rc=$?" | tee -a $O/summary.txt; }
-for v in vec1 vec2 wide wide2 stage tma; do
-T=300 run c5_$v env OGN_LARGE_VARIANT=$v python bench.py --no-cpu --workload c5 --steps 100
-done
-T=300 run c5_stage1 env OGN_LARGE_VARIANT=stage OGN_STAGE_CHUNKS=1 python bench.py --no-cpu --workload c5 --steps 100
-T=300 run c5_stage2 env OGN_LARGE_VARIANT=stage OGN_STAGE_CHUNKS=2 python bench.py --no-cpu --workload c5 --steps 100
+T=600 run t_ienc python -m pytest tests/test_image_encoder.py -m gpu -q
+T=300 run pipe256 python tools/bench_image_pipeline.py --size 256
+T=300 run pipe128 python tools/bench_image_pipeline.py --size 128
+T=300 run side1 env OGN_SIDE_STREAM=1 python bench.py --no-cpu --steps 60 --warmup 5
+T=300 run side0 python bench.py --no-cpu --steps 60 --warmup 5
+tail -n 5 $O/t_ienc.log; tail -n 1 $O/pipe256.log; tail -n 1 $O/pipe128.log
 python - <<'PY'
-import json,glob
-for f in sorted(glob.glob("gpurun_out/r3a/c5_*.log")):
+import json
+for f in ("side1","side0"):
     try:
-        d=json.loads(open(f).read().strip().splitlines()[-1])
-        k=d['roofline']['kernels']
-        print(f.split('/')[-1], round(d['value'],1), round(d['ms_per_step'],4), {n:round(v['ms_per_launch'],4) for n,v in k.items()}, d['state_hash']['crc32'])
-    except Exception as e: print(f, 'ERR', e)
+        d=json.loads(open(f"gpurun_out/r3b/{f}.log").read().strip().splitlines()[-1])
+        print(f, round(d['value'],1), round(d['ms_per_step'],4), d['state_hash']['crc32'])
+    except Exception as e: print(f,'ERR',e)
 PY

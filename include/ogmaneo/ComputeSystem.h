@@ -70,6 +70,10 @@ public:
     // Internal: lazily created device context (device ordinal + stream), shared with the layers created through it.
     detail::DeviceContext &context();
     std::shared_ptr<detail::DeviceContext> sharedContext() { context(); return ctx; }
+    // Run on `other`'s device and stream (call before the first layer is created through this system): objects made through
+    // two systems that share a context queue their kernels in program order on one stream, so one can consume the device
+    // buffers the other just produced without any synchronisation (ImageEncoder -> Hierarchy), while each keeps its own rng.
+    void shareContextWith(ComputeSystem &other) { ctx = other.sharedContext(); device = other.device; }
     // Block until all work queued on this system's stream has finished.
     void synchronize();
     // The cudaStream_t (as void*) the layers launch on.

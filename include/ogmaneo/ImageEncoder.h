@@ -56,6 +56,12 @@ public:
     void getReconstruction(int i, FloatBuffer &out) const;
     void stepHost(ComputeSystem &cs, const float *const *inputActs, bool learnEnabled); // raw pointers (what the C ABI calls)
     void reconstructHost(ComputeSystem &cs, const int *hiddenCs);
+    // device-resident step: inputActs[v] are DEVICE pointers (dense fp32, same layout); nothing is copied and nothing waits.
+    // The hidden CSDR is then at getHiddenCsDevice() on the system's stream, e.g. as an input of Hierarchy::stepDevice of a
+    // hierarchy created through the same ComputeSystem (or one that shares its context): image -> CSDR -> prediction
+    // without a host round trip.
+    void stepDevice(ComputeSystem &cs, const float *const *inputActsDevice, bool learnEnabled);
+    const int *getHiddenCsDevice() const;
     void readFromStream(std::istream &is, ComputeSystem &cs); // choose the device to load onto
 
 private:

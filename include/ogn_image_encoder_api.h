@@ -48,6 +48,19 @@ typedef struct ogn_ienc_visible_desc {
 
 OGN_DECLARE_IMAGE_ENCODER_API(ogn_)
 
+/* ---- device-resident extensions (CUDA product only; absent upstream) ----
+ * ogn_ienc_create_on: like ogn_ienc_create, but the encoder runs on the device and stream of `hierarchy` (a handle of
+ * include/ogn_hierarchy_api.h / ogn_b200.h, which must outlive the encoder); it keeps its own generator (seed).
+ * ogn_ienc_step_device: ImageEncoder::step on dense inputs that already live in device memory; asynchronous on that stream.
+ * ogn_ienc_hidden_cs_device: device pointer of the hidden CSDR (int32 per hidden column), valid for the life of the handle —
+ * hand it to ogn_step_device of the same hierarchy: image -> CSDR -> Hierarchy::step without a host round trip.
+ * ogn_ienc_synchronize: wait for the encoder's stream. */
+int ogn_ienc_create_on(void *hierarchy, int hidden_x, int hidden_y, int hidden_z, int num_visible, const ogn_ienc_visible_desc *descs,
+                       uint32_t seed, void **out);
+int ogn_ienc_step_device(void *e, const float *const *input_acts_dev, int learn_enabled);
+const int *ogn_ienc_hidden_cs_device(void *e);
+int ogn_ienc_synchronize(void *e);
+
 #ifdef __cplusplus
 }
 #endif

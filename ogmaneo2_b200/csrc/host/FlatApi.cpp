@@ -463,6 +463,26 @@ int ogn_ienc_create(int hx, int hy, int hz, int n, const ogn_ienc_visible_desc *
         *out = H.release();
     });
 }
+int ogn_ienc_create_on(void *hierarchy, int hx, int hy, int hz, int n, const ogn_ienc_visible_desc *d, uint32_t seed, void **out) {
+    *out = nullptr;
+    return guard([&] {
+        if (!hierarchy) throw std::invalid_argument("null hierarchy handle");
+        std::unique_ptr<IEncHandle> H(new IEncHandle());
+        H->cs.shareContextWith(((Handle *)hierarchy)->cs);
+        H->cs.rng.seed(seed);
+        std::vector<ImageEncoder::VisibleLayerDesc> vlds((size_t)n);
+        for (int v = 0; v < n; v++) { vlds[(size_t)v].size = Int3(d[v].size_x, d[v].size_y, d[v].size_z); vlds[(size_t)v].radius = d[v].radius; }
+        H->e.initRandom(H->cs, Int3(hx, hy, hz), vlds);
+        *out = H.release();
+    });
+}
+int ogn_ienc_step_device(void *e, const float *const *in, int learn) {
+    return guard([&] { IEncHandle *H = (IEncHandle *)e; H->e.stepDevice(H->cs, in, learn != 0); });
+}
+const int *ogn_ienc_hidden_cs_device(void *e) { return ((IEncHandle *)e)->e.getHiddenCsDevice(); }
+int ogn_ienc_synchronize(void *e) {
+    return guard([&] { ((IEncHandle *)e)->cs.synchronize(); });
+}
 void ogn_ienc_destroy(void *e) {
     try { delete (IEncHandle *)e; } catch (...) {}
 }

@@ -104,6 +104,24 @@ void ImageEncoder::stepHost(ComputeSystem &cs, const float *const *inputActs, bo
     if (learnEnabled) { m.resDirty = true; std::fill(m.wDirty.begin(), m.wDirty.end(), 1); }
 }
 
+void ImageEncoder::stepDevice(ComputeSystem &cs, const float *const *inputActsDevice, bool learnEnabled) {
+    Impl &m = *impl;
+    DeviceContext &ctx = *m.ctx;
+    cudaCheck(cudaSetDevice(ctx.device), "cudaSetDevice");
+    ogn_ienc_args a = m.args();
+    for (int v = 0; v < a.nvl; v++) {
+        if (!inputActsDevice[v]) throw std::invalid_argument("ogmaneo-b200: null device input");
+        a.vl[v].in = inputActsDevice[v];
+    }
+    consumeKernel2(cs, hiddenSize.x, hiddenSize.y);
+    kernelCheck(ogn_image_encoder_step(&a, hiddenSize.x, hiddenSize.y, hiddenSize.z, learnEnabled ? 1 : 0, alpha, gamma, m.resources.ptr(),
+                              m.hiddenCs.ptr(), ctx.stream), "ienc_step");
+    m.csDirty = true; // the host mirrors refresh (and wait) on demand
+    if (learnEnabled) { m.resDirty = true; std::fill(m.wDirty.begin(), m.wDirty.end(), 1); }
+}
+
+const int *ImageEncoder::getHiddenCsDevice() const { return impl ? impl->hiddenCs.ptr() : nullptr; }
+
 void ImageEncoder::step(ComputeSystem &cs, const std::vector<const FloatBuffer *> &inputActs, bool learnEnabled) {
     if (inputActs.size() != visibleLayerDescs.size()) throw std::invalid_argument("ogmaneo-b200: wrong number of dense inputs");
     std::vector<const float *> raw(inputActs.size());

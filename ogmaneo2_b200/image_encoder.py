@@ -65,6 +65,43 @@ class ImageEncoder:
             raise RuntimeError(f"{lib.prefix}ienc_create failed ({rc}): {lib.error()}")
 
     @classmethod
+    def createOn(cls, lib: IEncLib, hierarchy, hiddenSize, visibleLayers, seed: int = 1234):
+        """CUDA product only: an encoder on the device and stream of `hierarchy` (a `ogmaneo2_b200.Hierarchy`), so that
+        stepDevice() / hiddenCsDevice() feed hierarchy.stepDevice() without a host round trip."""
+        fn = getattr(lib.lib, lib.prefix + "ienc_create_on")
+        fn.restype = C.c_int
+        fn.argtypes = [_VP, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_CVisibleDesc), C.c_uint32, C.POINTER(_VP)]
+        vis = [(tuple(int(v) for v in s), int(r)) for s, r in visibleLayers]
+        d = (_CVisibleDesc * len(vis))()
+        for c, (s, r) in zip(d, vis):
+            c.size_x, c.size_y, c.size_z, c.radius = s[0], s[1], s[2], r
+        h = _VP()
+        rc = fn(hierarchy.h, *[int(v) for v in hiddenSize], len(vis), d, seed & 0xFFFFFFFF, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"{lib.prefix}ienc_create_on failed ({rc}): {lib.error()}")
+        obj = cls(lib, _handle=h)
+        obj.hiddenSize, obj.visible = tuple(int(v) for v in hiddenSize), vis
+        obj._keep = hierarchy  # the hierarchy owns the stream: keep it alive
+        return obj
+
+    def stepDevice(self, inputPtrs: Sequence[int], learnEnabled: bool = True):
+        """Dense inputs already in device memory (one pointer per visible layer); asynchronous."""
+        fn = getattr(self.f.lib, self.f.prefix + "ienc_step_device")
+        fn.restype, fn.argtypes = C.c_int, [_VP, C.POINTER(C.c_void_p), C.c_int]
+        ptrs = (C.c_void_p * len(inputPtrs))(*[int(p) for p in inputPtrs])
+        self._chk(fn(self.h, ptrs, int(learnEnabled)), "ienc_step_device")
+
+    def hiddenCsDevice(self) -> int:
+        fn = getattr(self.f.lib, self.f.prefix + "ienc_hidden_cs_device")
+        fn.restype, fn.argtypes = C.c_void_p, [_VP]
+        return int(fn(self.h))
+
+    def synchronize(self):
+        fn = getattr(self.f.lib, self.f.prefix + "ienc_synchronize")
+        fn.restype, fn.argtypes = C.c_int, [_VP]
+        self._chk(fn(self.h), "ienc_synchronize")
+
+    @classmethod
     def load(cls, lib: IEncLib, path: str, hiddenSize, visibleLayers):
         h = _VP()
         rc = lib.ienc_load(path.encode(), C.byref(h))

@@ -272,3 +272,38 @@ def test_device_ties_match_checker(product, name, tmp_path):
 @pytest.mark.gpu
 def test_device_matches_checker_at_bench_size(product):
     bench_size_pair(IEncLib(product.cdll(), "ogn_"), ref_lib() or port_lib(), steps=6)
+
+
+@pytest.mark.gpu
+def test_device_pipeline_image_to_prediction(product, tmp_path):
+    """ogn_ienc_create_on / ogn_ienc_step_device / ogn_ienc_hidden_cs_device: images in device memory -> ImageEncoder ->
+    Hierarchy::stepDevice on ONE stream, no host round trip and no synchronisation in between, against the checker's
+    ImageEncoder + Hierarchy driven through host buffers."""
+    import torch
+    from ogmaneo2_b200.flat_api import FlatHierarchy, InputType, LayerDesc
+    chk_flat, _ = loader.best()
+    hidden, visible = (8, 8, 16), [((16, 16, 3), 2)]
+    sizes, types = [hidden], [InputType.prediction]
+    lds = [LayerDesc(hiddenSize=(8, 8, 16), ffRadius=2, pRadius=2, ticksPerUpdate=2, temporalHorizon=2),
+           LayerDesc(hiddenSize=(6, 6, 16), ffRadius=2, pRadius=2, ticksPerUpdate=2, temporalHorizon=2)]
+    dev_h = product.Hierarchy(sizes, types, lds, seed=11)
+    dev_e = ImageEncoder.createOn(IEncLib(product.cdll(), "ogn_"), dev_h, hidden, visible, seed=77)
+    ref_h = FlatHierarchy(chk_flat, sizes, types, lds, 11)
+    ref_e = ImageEncoder(ref_lib() or port_lib(), hidden, visible, seed=77)
+    case = dict(hidden=hidden, visible=visible)
+    frames = [torch.from_numpy(dense_input(case, t, 0)).cuda() for t in range(24)]
+    torch.cuda.synchronize()
+    for t in range(24):  # queue everything; nothing waits inside the loop
+        dev_e.stepDevice([frames[t].data_ptr()], True)
+        dev_h.stepDevice([dev_e.hiddenCsDevice()], True)
+        if t % 8 == 7:
+            want_cs = None
+            for u in range(t - 7, t + 1):
+                ref_e.step([dense_input(case, u, 0)], True)
+                want_cs = ref_e.getHiddenCs()
+                ref_h.step([want_cs], True)
+            assert np.array_equal(dev_e.getHiddenCs(), want_cs), f"encoder CSDR differs at step {t}"
+            assert np.array_equal(dev_h.getPredictionCs(0), ref_h.getPredictionCs(0)), f"prediction differs at step {t}"
+    d = diff_snapshots(dev_e.snapshot(), ref_e.snapshot())
+    assert not d, d[:3]
+    ref_h.close()
