@@ -155,7 +155,8 @@ typedef struct ogn_actor_batch {
 typedef struct ogn_small_phase {
     int kind;                 /* OGN_PHASE_* */
     int z;                    /* row width of the phase's 128-bit kernels: Hz (forward, Predictor) or Vz (reconstruction, update) */
-    int reserved;
+    int unitShift;            /* first of the launch's unit slots (warps, wide mapping) this phase starts on: the phases between two
+                                 barriers are independent, and disjoint slot ranges make them run side by side */
     int barrierAfter;         /* 1: the blocks of a member meet before the next phase starts */
     int counter;              /* work-list slot (reconstruction / update pairs share one) */
     int Hx, Hy;               /* grid the packs tile: hidden grid (forward, Predictor), visible grid (reconstruction) */

@@ -35,6 +35,7 @@ struct StepGraph {
 struct SmallStep {
     DevBuf<ogn_small_phase> phases;
     int nphases = 0;
+    int blocks = 1; // blocks per member of this step's launch
 };
 
 struct Hierarchy::Impl {
@@ -437,9 +438,24 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
             }
             std::stable_sort(order.begin(), order.end());
             std::vector<ogn_small_phase> ph(order.size());
+            // unit slots: inside a level every phase starts where the previous one's units end (update phases, whose unit
+            // count is data-dependent, come last in their level), and the launch gets enough blocks for its widest level
+            static const int spread = std::getenv("OGN_SMALL_SPREAD") ? std::atoi(std::getenv("OGN_SMALL_SPREAD")) : 1;
+            int shift = 0, widest = 0;
             for (size_t i = 0; i < order.size(); i++) {
                 ph[i] = plan.nodes[order[i].second].ph;
                 ph[i].barrierAfter = (i + 1 < order.size() && order[i + 1].first / 4 != order[i].first / 4) ? 1 : 0;
+                ph[i].unitShift = (spread && m.smallWide && m.smallBlocks > 1) ? shift : 0;
+                const int units = ph[i].kind == OGN_PHASE_SC_RECON ? ph[i].npacks * ph[i].u.learn.nvl
+                                  : ph[i].kind == OGN_PHASE_SC_UPDATE ? ph[i].npacks : ph[i].npacks;
+                shift += units;
+                widest = std::max(widest, shift);
+                if (ph[i].barrierAfter) shift = 0;
+            }
+            ss.blocks = m.smallBlocks;
+            if (spread && m.smallWide && m.smallBlocks > 1) {
+                const int cap = ogn_hier_small_max_blocks(m.smallThreads);
+                ss.blocks = std::max(m.smallBlocks, std::min((widest + 7) / 8, cap));
             }
             ss.phases.alloc(ph.size());
             cudaCheck(cudaMemcpyAsync(ss.phases.ptr(), ph.data(), ph.size() * sizeof(ogn_small_phase), cudaMemcpyHostToDevice, ctx.stream),
@@ -452,7 +468,7 @@ void Hierarchy::stepImpl(ComputeSystem &cs, const int *const *hostIn, const std:
             ctx.dry = false; ctx.dryUncounted = false;
         }
         LaunchScope ls(ctx, kHierSmall);
-        kernelCheck(ogn_hier_step_small(ss.phases.ptr(), ss.nphases, &smallIn, m.batch, m.smallBlocks, m.smallThreads, m.smallWide,
+        kernelCheck(ogn_hier_step_small(ss.phases.ptr(), ss.nphases, &smallIn, m.batch, ss.blocks, m.smallThreads, m.smallWide,
                                         m.smallCounters.ptr(), ctx.stream), "hier_step_small");
         return;
     }

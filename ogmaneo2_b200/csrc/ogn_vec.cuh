@@ -1025,11 +1025,10 @@ __device__ __noinline__ void small_recon(const ogn_small_phase &P, int member, i
     }
 }
 template <int Z, int VER, class CS>
-__device__ __noinline__ void small_update(const ogn_small_phase &P, int member, int nb, unsigned *cnt) {
+__device__ __noinline__ void small_update(const ogn_small_phase &P, int member, int warp, int nwarps, unsigned *cnt) {
     const int ITEMS = VER == 2 ? UpdV2<Z>::ITEMS * P.updBatches : UpdV1<Z>::ITEMS;
     const int2 *work = reinterpret_cast<const int2 *>(P.work) + (long long)member * P.workStride;
     const unsigned n = __ldcg(cnt);
-    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = nb * (blockDim.x >> 5);
     const long long nunits = (long long)n * P.chunks;
     int nupd = 0;
     for (long long unit = warp; unit < nunits; unit += nwarps) {
@@ -1083,31 +1082,38 @@ k_hier_step_small(const ogn_small_phase *__restrict__ phases, int nphases, const
     __syncthreads();
     // units of this block: octets (W = 8) or warps (W = 32), strided over the member's blocks
     const int unitsPerBlock = blockDim.x / W, unit0 = blockIdx.x * unitsPerBlock + threadIdx.x / W, stride = nb * unitsPerBlock;
+    const int warpsPerBlock = blockDim.x >> 5, nwarps = nb * warpsPerBlock;
     for (int ph = 0; ph < nphases; ++ph) {
         const ogn_small_phase &P = phases[ph];
         unsigned *cnt = mc + 2 + P.counter;
+        // the phases between two barriers are independent: each starts on its own range of the launch's unit slots
+        // (unitShift), so a slot that has nothing to do in one phase is already working on the next one
+        int u0 = unit0 - P.unitShift % stride;
+        if (u0 < 0) u0 += stride;
+        int w0 = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5) - P.unitShift % nwarps;
+        if (w0 < 0) w0 += nwarps;
         switch (P.kind) {
         case OGN_PHASE_SC_FORWARD:
-            OGN_SMALL_Z((small_fwd<8, W, CS>(P, member, unit0, stride)), (small_fwd<16, W, CS>(P, member, unit0, stride)),
-                        (small_fwd<32, W, CS>(P, member, unit0, stride)));
+            OGN_SMALL_Z((small_fwd<8, W, CS>(P, member, u0, stride)), (small_fwd<16, W, CS>(P, member, u0, stride)),
+                        (small_fwd<32, W, CS>(P, member, u0, stride)));
             break;
         case OGN_PHASE_SC_RECON:
-            OGN_SMALL_Z((small_recon<8, W, CS>(P, member, unit0, stride, cnt)), (small_recon<16, W, CS>(P, member, unit0, stride, cnt)),
-                        (small_recon<32, W, CS>(P, member, unit0, stride, cnt)));
+            OGN_SMALL_Z((small_recon<8, W, CS>(P, member, u0, stride, cnt)), (small_recon<16, W, CS>(P, member, u0, stride, cnt)),
+                        (small_recon<32, W, CS>(P, member, u0, stride, cnt)));
             break;
         case OGN_PHASE_SC_UPDATE:
             if (P.updVer == 2) {
-                OGN_SMALL_Z((small_update<8, 2, CS>(P, member, nb, cnt)), (small_update<16, 2, CS>(P, member, nb, cnt)),
-                            (small_update<32, 2, CS>(P, member, nb, cnt)));
+                OGN_SMALL_Z((small_update<8, 2, CS>(P, member, w0, nwarps, cnt)), (small_update<16, 2, CS>(P, member, w0, nwarps, cnt)),
+                            (small_update<32, 2, CS>(P, member, w0, nwarps, cnt)));
             } else {
-                OGN_SMALL_Z((small_update<8, 1, CS>(P, member, nb, cnt)), (small_update<16, 1, CS>(P, member, nb, cnt)),
-                            (small_update<32, 1, CS>(P, member, nb, cnt)));
+                OGN_SMALL_Z((small_update<8, 1, CS>(P, member, w0, nwarps, cnt)), (small_update<16, 1, CS>(P, member, w0, nwarps, cnt)),
+                            (small_update<32, 1, CS>(P, member, w0, nwarps, cnt)));
             }
             break;
         case OGN_PHASE_PRED:
             if (P.activate == 1) pred_copy_inputs<CS>(P.u.pred, member, blockIdx.x * blockDim.x + threadIdx.x, nb * blockDim.x);
-            OGN_SMALL_Z((small_pred<8, W, CS>(P, member, unit0, stride)), (small_pred<16, W, CS>(P, member, unit0, stride)),
-                        (small_pred<32, W, CS>(P, member, unit0, stride)));
+            OGN_SMALL_Z((small_pred<8, W, CS>(P, member, u0, stride)), (small_pred<16, W, CS>(P, member, u0, stride)),
+                        (small_pred<32, W, CS>(P, member, u0, stride)));
             break;
         default: break;
         }
