@@ -316,6 +316,8 @@ int ogn_weights_fr_mismatch(const ogn_wset *wset_host, const ogn_rf *rf_host, in
 void ogn_debug_variant_launches(long long out[24]);
 /* debug timeline of the tile-staged ImageEncoder kernel: see ogn_kernels.cu */
 int ogn_debug_ienc_trace(int blocks, long long *out);
+/* debug timeline of the single-launch step (ogn_hier_step_small): see ogn_kernels.cu */
+int ogn_debug_small_trace(int arm, unsigned long long *out);
 
 /* Device replays of glibc expf/tanhf (csrc/ogn_libm.h), exposed for tests: out[i] = f(in[i]). */
 int ogn_test_expf(const float *in, float *out, int64_t n, void *stream);

@@ -1389,6 +1389,7 @@ static int vec_threads(int variant) { // threads per block of the 128-bit kernel
 // a size actually ran (ogn_debug_variant_launches)
 static long long g_variantLaunches[3][8];
 static long long *g_iencTrace = nullptr; // ogn_debug_ienc_trace
+static unsigned long long *g_smallTrace = nullptr; // ogn_debug_small_trace
 static int g_iencTraceBlocks = 0;
 static void count_variant(int kernel, int variant) {
     const int col = variant == kVarScalar ? 0 : variant == kVarVec1 ? 1 : variant == kVarVec2 ? 2 : variant == kVarStage ? 3 : variant == kVarTma ? 5 : variant == kVarWide ? 6 : 7;
@@ -1700,11 +1701,12 @@ int ogn_hier_step_small(const ogn_small_phase *phases, int nphases, const ogn_sm
     if (phaseBytes > 48 * 1024) phaseBytes = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (blocks_per_member == 1) { // one block owns a member: CSDRs written by the block are read back through its own L1
-        if (wide) vec::k_hier_step_small<32, vec::CsSm><<<grid, threads, phaseBytes, st>>>(phases, nphases, in, counters, cpm, phaseBytes);
-        else vec::k_hier_step_small<8, vec::CsSm><<<grid, threads, phaseBytes, st>>>(phases, nphases, in, counters, cpm, phaseBytes);
+        if (wide) vec::k_hier_step_small<32, vec::CsSm><<<grid, threads, phaseBytes, st>>>(phases, nphases, in, counters, cpm, phaseBytes, g_smallTrace);
+        else vec::k_hier_step_small<8, vec::CsSm><<<grid, threads, phaseBytes, st>>>(phases, nphases, in, counters, cpm, phaseBytes, g_smallTrace);
         return launch_status();
     }
-    void *kargs[] = {(void *)&phases, (void *)&nphases, (void *)&in, (void *)&counters, (void *)&cpm, (void *)&phaseBytes};
+    unsigned long long *trace = g_smallTrace;
+    void *kargs[] = {(void *)&phases, (void *)&nphases, (void *)&in, (void *)&counters, (void *)&cpm, (void *)&phaseBytes, (void *)&trace};
     const void *fn = wide ? (const void *)vec::k_hier_step_small<32, vec::CsCg> : (const void *)vec::k_hier_step_small<8, vec::CsCg>;
     return (int)cudaLaunchCooperativeKernel(fn, grid, dim3((unsigned)threads), kargs, (size_t)phaseBytes, st);
 }
@@ -1797,6 +1799,25 @@ int ogn_weights_fr_mismatch(const ogn_wset *ws, const ogn_rf *rf, int member, un
                                                                         ws->wr + (long long)member * ws->wr_mstride, ws->wr_base,
                                                                         xa * rf->Hy, count_dev);
     return launch_status();
+}
+
+// Timeline of the single-launch step: (1, NULL) arms a device buffer of 2 x 256 x 3 globaltimer stamps (blocks 0 and nb - 1 of
+// member 0; per phase: start, end of the phase's work, end of its barrier), overwritten by every launch; (0, out) copies the
+// 1536 words to the host and disarms. Returns 0 or a CUDA error.
+int ogn_debug_small_trace(int arm, unsigned long long *out) {
+    if (arm) {
+        if (!g_smallTrace) {
+            cudaError_t e = cudaMalloc(&g_smallTrace, 1536 * sizeof(unsigned long long));
+            if (e != cudaSuccess) return (int)e;
+        }
+        return (int)cudaMemset(g_smallTrace, 0, 1536 * sizeof(unsigned long long));
+    }
+    if (!g_smallTrace) return (int)cudaErrorInvalidValue;
+    cudaDeviceSynchronize();
+    cudaError_t e = out ? cudaMemcpy(out, g_smallTrace, 1536 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) : cudaSuccess;
+    cudaFree(g_smallTrace);
+    g_smallTrace = nullptr;
+    return (int)e;
 }
 
 // Timeline of the tile-staged ImageEncoder kernel: (blocks, NULL) arms a device buffer of 12 words per block (stamps 0..7 =

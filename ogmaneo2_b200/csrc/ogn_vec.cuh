@@ -1064,8 +1064,13 @@ __device__ __noinline__ void small_pred(const ogn_small_phase &P, int member, in
 template <int W, class CS>
 __global__ void __launch_bounds__(512, 1)
 k_hier_step_small(const ogn_small_phase *__restrict__ phases, int nphases, const __grid_constant__ ogn_small_inputs I, unsigned *counters,
-                  int countersPerMember, int phaseBytes) {
+                  int countersPerMember, int phaseBytes, unsigned long long *trace) {
     const int member = blockIdx.y, nb = gridDim.x;
+    // debug timeline (ogn_debug_small_trace): thread 0 of blocks 0 and nb - 1 of member 0 stamps globaltimer at the start of
+    // every phase, after it and after its barrier: trace[(block ? 1 : 0) * 3 * 256 + 3 * ph + {0, 1, 2}]
+    const bool tr = trace && threadIdx.x == 0 && blockIdx.y == 0 && (blockIdx.x == 0 || (int)blockIdx.x == nb - 1);
+    unsigned long long *tb = trace + (blockIdx.x ? 768 : 0);
+#define SMALL_STAMP(i) do { if (tr && ph < 256) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tb[3 * ph + (i)] = t_; } } while (0)
     unsigned *mc = counters + (long long)member * countersPerMember;
     if (phaseBytes > 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(phases);
@@ -1086,6 +1091,7 @@ k_hier_step_small(const ogn_small_phase *__restrict__ phases, int nphases, const
     for (int ph = 0; ph < nphases; ++ph) {
         const ogn_small_phase &P = phases[ph];
         unsigned *cnt = mc + 2 + P.counter;
+        SMALL_STAMP(0);
         // the phases between two barriers are independent: each starts on its own range of the launch's unit slots
         // (unitShift), so a slot that has nothing to do in one phase is already working on the next one
         int u0 = unit0 - P.unitShift % stride;
@@ -1117,8 +1123,11 @@ k_hier_step_small(const ogn_small_phase *__restrict__ phases, int nphases, const
             break;
         default: break;
         }
+        SMALL_STAMP(1);
         if (ph + 1 < nphases && P.barrierAfter) member_barrier(mc, nb);
+        SMALL_STAMP(2);
     }
+#undef SMALL_STAMP
     // the work-list fills go back to zero for the next launch: a reconstruction is always followed by its update behind a
     // barrier, so after one more barrier nobody reads a fill any more
     member_barrier(mc, nb);
