@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <map>
 #include <set>
 
 #include "../../include/ogn_kernels_api.h"
@@ -1397,15 +1398,19 @@ static void count_variant(int kernel, int variant) {
 }
 
 } // extern "C"
-// <<<>>> with dynamic shared memory above the 48 KB default opted in once per kernel
+// <<<>>> with dynamic shared memory above the 48 KB default opted in per kernel (again whenever a launch needs more than
+// any earlier one of the same kernel did)
 template <typename... P, typename... A>
 static void launch_k(void (*k)(P...), dim3 grid, int threads, size_t smem, cudaStream_t st, A... a) {
     if (smem > 48u * 1024u) {
         static std::mutex mtx;
-        static std::set<const void *> done;
+        static std::map<const void *, size_t> optedIn;
         std::lock_guard<std::mutex> lock(mtx);
-        if (done.insert((const void *)k).second)
+        size_t &have = optedIn[(const void *)k];
+        if (smem > have) {
             cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            have = smem;
+        }
     }
     k<<<grid, threads, smem, st>>>(a...);
 }
@@ -1649,18 +1654,14 @@ int ogn_image_encoder_step(const ogn_ienc_args *args, int Hx, int Hy, int Hz, in
     L.barOff = floats;
     const size_t smem = (size_t)floats * 4 + 8 * (size_t)OGN_MAX_IENC_VL;
     if (useTile && (P * Hz) % 4 == 0 && smem <= 200 * 1024) {
-        bool ok = true;
         const cudaStream_t st = (cudaStream_t)stream;
+        const dim3 grid((unsigned)npacks);
         if (P * Hz == 32) {
-            OGN_DISPATCH_G(g, (ok = cudaFuncSetAttribute(k_ienc_step_t<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess));
-            if (!ok) return (int)cudaGetLastError();
-            OGN_DISPATCH_G(g, (k_ienc_step_t<G, true><<<(unsigned)npacks, 32, smem, st>>>(*args, L, Hx, Hy, Hz, ppr, learn, alpha, gamma, resources,
-                                                                                        hidden_cs, g_iencTrace, g_iencTraceBlocks)));
+            OGN_DISPATCH_G(g, (launch_k(k_ienc_step_t<G, true>, grid, 32, smem, st, *args, L, Hx, Hy, Hz, ppr, learn, alpha, gamma, resources, hidden_cs,
+                                        g_iencTrace, g_iencTraceBlocks)));
         } else {
-            OGN_DISPATCH_G(g, (ok = cudaFuncSetAttribute(k_ienc_step_t<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess));
-            if (!ok) return (int)cudaGetLastError();
-            OGN_DISPATCH_G(g, (k_ienc_step_t<G, false><<<(unsigned)npacks, 32, smem, st>>>(*args, L, Hx, Hy, Hz, ppr, learn, alpha, gamma, resources,
-                                                                                         hidden_cs, g_iencTrace, g_iencTraceBlocks)));
+            OGN_DISPATCH_G(g, (launch_k(k_ienc_step_t<G, false>, grid, 32, smem, st, *args, L, Hx, Hy, Hz, ppr, learn, alpha, gamma, resources, hidden_cs,
+                                        g_iencTrace, g_iencTraceBlocks)));
         }
         return launch_status();
     }

@@ -17,6 +17,8 @@ CASES = {
     "z32": dict(hidden=(4, 6, 32), visible=[((8, 6, 1), 2)]),                        # 32 cells per column (std::sort past its insertion-sort size)
     "odd": dict(hidden=(3, 4, 5), visible=[((7, 3, 2), 1)]),                         # Z off the powers of two
     "z18": dict(hidden=(3, 3, 18), visible=[((6, 6, 2), 2)]),                        # row of 18 floats: not bulk-copyable, two-pass kernel
+    "big_field": dict(hidden=(4, 4, 32), visible=[((16, 16, 4), 5)]),                # 62 KB block per pack: shared memory above the 48 KB default
+    "bigger_field": dict(hidden=(3, 3, 32), visible=[((16, 16, 4), 6)]),             # 86 KB: the opt-in has to grow within one process
 }
 
 
