@@ -1,7 +1,20 @@
 cd /root/repo
-O=gpurun_out/r3f; mkdir -p $O
+O=gpurun_out/r3g; mkdir -p $O
 run() { name=$1; shift; timeout "${T:-300}" "$@" > $O/$name.log 2>&1; echo "$name rc=$?" | tee -a $O/summary.txt; }
-T=600 run t_ienc python -m pytest tests/test_image_encoder.py -m gpu -q
-T=600 run t_stage python -m pytest -m gpu -q "tests/test_gpu_parity.py::test_every_kernel_variant_and_scheduling_mode_is_bit_exact[kernels=stage]" "tests/test_gpu_parity.py::test_every_kernel_variant_and_scheduling_mode_is_bit_exact[kernels=tma]"
-T=300 run ienc python tools/bench_image_encoder.py
-tail -n 3 $O/t_ienc.log $O/t_stage.log; tail -n 1 $O/ienc.log | cut -c1-200
+B="python bench.py --no-cpu --size 184 --steps 300"
+T=200 run s184_default $B
+T=200 run s184_t128 env OGN_VEC_THREADS=128 $B
+T=200 run s184_t64 env OGN_VEC_THREADS=64 $B
+T=200 run s184_stage env OGN_LARGE_VARIANT=stage $B
+T=200 run s184_stage_t128 env OGN_LARGE_VARIANT=stage OGN_VEC_THREADS=128 $B
+T=200 run s184_side env OGN_SIDE_STREAM=1 $B
+T=200 run s184_side_t128 env OGN_SIDE_STREAM=1 OGN_VEC_THREADS=128 $B
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/r3g/s184_*.log")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        k=d['roofline']['kernels']
+        print(f.split('/')[-1], round(d['value'],1), round(d['ms_per_step'],4), {n:round(v['ms_per_launch'],4) for n,v in k.items()}, d['state_hash']['crc32'])
+    except Exception as e: print(f, 'ERR', e)
+PY
