@@ -1,3 +1,5 @@
+# scratch driver of the last single-GPU measurement call of round 2 (run from the repo root: bash tools/gpu_run_last.sh); the
+# commands behind every committed artifact are in profiles/commands.md
 cd /root/repo
 O=gpurun_out/r3i; mkdir -p $O
 run() { name=$1; shift; timeout "${T:-300}" "$@" > $O/$name.log 2>&1; echo "$name rc=$?" | tee -a $O/summary.txt; }
