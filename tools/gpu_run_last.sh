@@ -1,9 +1,12 @@
 # scratch driver of the last single-GPU measurement call of round 2 (run from the repo root: bash tools/gpu_run_last.sh); the
 # commands behind every committed artifact are in profiles/commands.md
 cd /root/repo
-O=gpurun_out/r3j; mkdir -p $O
-CMD="python bench.py --no-cpu --steps 10 --warmup 5 --burnin 100"
-$CMD > $O/ncu_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'k_(sc|pred)' -s 400 -c 4 -o $O/prof_c4_512_final $CMD > $O/ncu_full.log 2>&1
-echo "ncu rc=$?"
-tail -n 2 $O/ncu_full.log | cut -c1-300
+O=gpurun_out/r3k; mkdir -p $O
+timeout 200 env OGN_SMALL_KERNEL=1 python tools/trace_small_step.py --workload c1 > $O/trace_c1.json 2> $O/trace_c1.err; echo "rc=$?"
+tail -c 300 $O/trace_c1.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r3k/trace_c1.json").read().strip().splitlines()[-1])
+for s in d[:8]:
+    print(s['step'], s['phases'], s['total_us'], [(r['work_us'], r['barrier_us']) for r in s['rows']])
+PY
