@@ -1024,9 +1024,13 @@ k_ienc_step_t(const __grid_constant__ ogn_ienc_args A, const __grid_constant__ I
     const int pack = blockIdx.x;
     const unsigned gm = lane_mask<G>();
     const int ox = pack / packsPerRow, q = pack % packsPerRow;
-    const int p = gl / G, hc = gl % G;
+    // a pack occupies GP = G * P lanes (32 for 8 or more cells per column, 16 / 8 / 4 below): the warp's other lanes mirror
+    // lanes [0, GP) for the collective operations and own no column
+    constexpr int GP = Pack<G>::GP;
+    const int gle = gl % GP;
+    const int p = gle / G, hc = gle % G;
     const int oy = q * P + p;
-    const bool colValid = oy < Hy, act = colValid && hc < Hz;
+    const bool colValid = gl < GP && oy < Hy, act = colValid && hc < Hz;
     const long long col = (long long)ox * Hy + (colValid ? oy : Hy - 1);
     const int rowW = P * Hz;
     const int li = p * Hz + (hc < Hz ? hc : Hz - 1);

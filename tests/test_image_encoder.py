@@ -309,3 +309,32 @@ def test_device_pipeline_image_to_prediction(product, tmp_path):
     d = diff_snapshots(dev_e.snapshot(), ref_e.snapshot())
     assert not d, d[:3]
     ref_h.close()
+
+
+def random_cases(n=10, seed=2024):
+    """Seeded random encoder geometries: column heights on and off the powers of two (pack factors 1..8, rows that are and are
+    not 128 bytes), one or two dense inputs of unrelated sizes, radii up to 3."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        hz = int(rng.choice([2, 3, 4, 5, 8, 12, 16, 20, 24, 32]))
+        hidden = (int(rng.randint(2, 8)), int(rng.randint(2, 8)), hz)
+        vis = []
+        for _v in range(int(rng.randint(1, 3))):
+            vis.append(((int(rng.randint(3, 15)), int(rng.randint(3, 15)), int(rng.randint(1, 5))), int(rng.randint(1, 4))))
+        out.append(dict(hidden=hidden, visible=vis))
+    return out
+
+
+@pytest.mark.parametrize("i", range(10))
+def test_port_matches_reference_random_shapes(i, tmp_path):
+    ref = ref_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no reference sources on this box)")
+    run_pair(random_cases()[i], port_lib(), ref, steps=8, tmp_path=tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(10))
+def test_device_matches_checker_random_shapes(product, i, tmp_path):
+    run_pair(random_cases()[i], IEncLib(product.cdll(), "ogn_"), ref_lib() or port_lib(), steps=8, tmp_path=tmp_path)
