@@ -202,12 +202,15 @@ def test_random_shapes_inner(product, oracle, seed):
     _check(product, oracle, random_cfg(seed), 24, check_every=4)
 
 
-# A subprocess, so that a device fault on one odd shape cannot poison the CUDA context of the tests that follow.
-def test_random_shapes():
+# A subprocess, so that a device fault on one odd shape cannot poison the CUDA context of the tests that follow. Besides the
+# default selection the random geometries also run with the opt-in paths that have code of their own per shape class.
+@pytest.mark.parametrize("env", [{}, {"OGN_SMALL_KERNEL": "1"}, {"OGN_KERNELS": "tma"}, {"OGN_KERNELS": "stage"}, {"OGN_KERNELS": "wide2"}],
+                         ids=lambda e: "-".join(f"{k[4:].lower()}={v}" for k, v in e.items()) or "default")
+def test_random_shapes(env):
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-k", "random_shapes_inner"]
-    r = subprocess.run(cmd, cwd=root, env=dict(os.environ, OGN_RUN_RANDOM_SHAPES="1"), capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, cwd=root, env=dict(os.environ, OGN_RUN_RANDOM_SHAPES="1", **env), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-1000:]
