@@ -257,3 +257,66 @@ class Hierarchy:
     def setAMinSteps(self, v: int, x: int): self.getALayers()[v].minSteps = x
     def getAHistoryIters(self, v: int) -> int: return self._h.getActorParams(v)["historyIters"]
     def setAHistoryIters(self, v: int, x: int): self.getALayers()[v].historyIters = x
+
+
+class ImageEncoderVisibleLayerDesc:
+    """ogmaneo::ImageEncoder::VisibleLayerDesc (ImageEncoder.h:21-33), same member names and defaults."""
+
+    def __init__(self, size: Int3 = None, radius: int = 2):
+        self.size = size if size is not None else Int3(4, 4, 16)
+        self.radius = radius
+
+
+class ImageEncoder:
+    """ogmaneo::ImageEncoder (ImageEncoder.h:18-154) on the CUDA path: construct with (cs, hiddenSize, visibleLayerDescs) —
+    initRandom — or with (cs, fileName, hiddenSize=..., visibleLayerDescs=...) — readFromStream. `alpha` and `gamma` are the
+    public members of the reference (defaults 0.01). With `hierarchy=` the encoder runs on that hierarchy's stream, so its
+    hidden CSDR can feed `hierarchy.step` without leaving the device (stepDevice / hiddenCsDevice of the wrapped object)."""
+
+    def __init__(self, cs: ComputeSystem, hiddenSize_or_file, visibleLayerDescs: Sequence[ImageEncoderVisibleLayerDesc] = None,
+                 hiddenSize: Int3 = None, hierarchy: "Hierarchy" = None):
+        from . import cdll
+        from . import image_encoder as _ienc
+        lib = _ienc.IEncLib(cdll(), "ogn_")
+        vis = [(tuple(d.size), int(d.radius)) for d in (visibleLayerDescs or [])]
+        self._alpha, self._gamma = 0.01, 0.01
+        if isinstance(hiddenSize_or_file, str):
+            self._e = _ienc.ImageEncoder.load(lib, hiddenSize_or_file, tuple(hiddenSize), vis)
+        elif hierarchy is not None:
+            self._e = _ienc.ImageEncoder.createOn(lib, hierarchy._h, tuple(hiddenSize_or_file), vis, seed=cs.seed)
+        else:
+            self._e = _ienc.ImageEncoder(lib, tuple(hiddenSize_or_file), vis, seed=cs.seed)
+
+    alpha = property(lambda self: self._alpha, lambda self, v: self._set(alpha=v))
+    gamma = property(lambda self: self._gamma, lambda self, v: self._set(gamma=v))
+
+    def _set(self, alpha=None, gamma=None):
+        self._alpha = self._alpha if alpha is None else float(alpha)
+        self._gamma = self._gamma if gamma is None else float(gamma)
+        self._e.setParams(self._alpha, self._gamma)
+
+    def step(self, cs: ComputeSystem, inputActs: Sequence[Sequence[float]], learnEnabled: bool = True):
+        self._e.step([np.asarray(a, dtype=np.float32) for a in inputActs], learnEnabled)
+
+    def reconstruct(self, cs: ComputeSystem, hiddenCs: Sequence[int]):
+        self._e.reconstruct(np.asarray(hiddenCs, dtype=np.int32))
+
+    def getHiddenCs(self) -> List[int]:
+        return self._e.getHiddenCs().tolist()
+
+    def getReconstruction(self, i: int) -> List[float]:
+        return self._e.getReconstruction(i).tolist()
+
+    def getHiddenSize(self) -> Int3:
+        return Int3(*self._e.hiddenSize)
+
+    def getNumVisibleLayers(self) -> int:
+        return len(self._e.visible)
+
+    def getVisibleLayerDesc(self, i: int) -> ImageEncoderVisibleLayerDesc:
+        s, r = self._e.visible[i]
+        return ImageEncoderVisibleLayerDesc(Int3(*s), r)
+
+    def save(self, fileName: str) -> int:
+        """ImageEncoder::writeToStream into a file (same bytes as the reference writes)."""
+        return self._e.save(fileName)

@@ -338,3 +338,42 @@ def test_port_matches_reference_random_shapes(i, tmp_path):
 @pytest.mark.parametrize("i", range(10))
 def test_device_matches_checker_random_shapes(product, i, tmp_path):
     run_pair(random_cases()[i], IEncLib(product.cdll(), "ogn_"), ref_lib() or port_lib(), steps=8, tmp_path=tmp_path)
+
+
+@pytest.mark.gpu
+def test_pyogmaneo_style_image_encoder(product, tmp_path):
+    """pyogmaneo.ImageEncoder (names of the reference's Python binding) against the checker: step, reconstruct, parameters,
+    save / load, and the device-chained form (hierarchy=...)."""
+    from ogmaneo2_b200 import pyogmaneo as po
+    case = CASES["rgb"]
+    cs = po.ComputeSystem(seed=77)
+    descs = [po.ImageEncoderVisibleLayerDesc(po.Int3(*s), r) for s, r in case["visible"]]
+    enc = po.ImageEncoder(cs, po.Int3(*case["hidden"]), descs)
+    chk = ImageEncoder(ref_lib() or port_lib(), case["hidden"], case["visible"], seed=77)
+    enc.alpha, enc.gamma = 0.05, 0.2
+    chk.setParams(0.05, 0.2)
+    assert (enc.alpha, enc.gamma) == (0.05, 0.2) and tuple(enc.getHiddenSize()) == tuple(case["hidden"])
+    assert enc.getNumVisibleLayers() == 1 and enc.getVisibleLayerDesc(0).radius == case["visible"][0][1]
+    for t in range(6):
+        x = dense_input(case, t, 0)
+        enc.step(cs, [x.tolist()], True)
+        chk.step([x], True)
+        assert enc.getHiddenCs() == chk.getHiddenCs().tolist(), f"step {t}"
+    enc.reconstruct(cs, enc.getHiddenCs())
+    chk.reconstruct(chk.getHiddenCs())
+    assert np.array_equal(np.asarray(enc.getReconstruction(0), np.float32).view(np.int32), chk.getReconstruction(0).view(np.int32))
+    f = str(tmp_path / "e.ienc")
+    assert enc.save(f) > 0
+    again = po.ImageEncoder(cs, f, descs, hiddenSize=po.Int3(*case["hidden"]))
+    again.alpha, again.gamma = 0.05, 0.2
+    x = dense_input(case, 6, 0)
+    again.step(cs, [x], True)
+    chk.step([x], True)
+    assert again.getHiddenCs() == chk.getHiddenCs().tolist()
+    # chained on a hierarchy's stream
+    lds = [po.LayerDesc(po.Int3(6, 5, 16))]
+    h = po.Hierarchy(cs, [po.Int3(*case["hidden"])], [po.inputTypePrediction], lds)
+    enc2 = po.ImageEncoder(cs, po.Int3(*case["hidden"]), descs, hierarchy=h)
+    enc2.step(cs, [dense_input(case, 0, 0)], True)
+    h.step(cs, [enc2.getHiddenCs()], True)
+    assert len(h.getPredictionCs(0)) == case["hidden"][0] * case["hidden"][1]
