@@ -701,6 +701,13 @@ def main():
                                     "independent of --gpus for the same --steps/--warmup"},
            "ranks": ranks_info, "host_enqueue_ms_per_step": host_enqueue_ms,
            "column_steps_per_s": value * sum(ld.hiddenSize[0] * ld.hiddenSize[1] * c for ld, c in zip(cfg["layerDescs"], counts)) / K}
+    if args.workload == "c1" and world == 1:
+        # a fresh hierarchy run for the contract's 10 000 steps; mispredicted steps among the last 1000
+        # (19 for the reference on this stream; tests/test_oracle.py::test_c1_learns_the_sine_wave pins it). Untimed.
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from common import c1_last1000_errors
+        fresh = og.Hierarchy(cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], seed=cfg["seed"])
+        out["c1_last1000_prediction_errors"] = {"value": c1_last1000_errors(fresh, cfg), "reference": 19, "steps": 10000}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

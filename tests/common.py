@@ -73,3 +73,17 @@ def maker(flat):
     def mk(cfg):
         return FlatHierarchy(flat, cfg["inputSizes"], cfg["inputTypes"], cfg["layerDescs"], cfg["seed"])
     return mk
+
+
+def c1_last1000_errors(h, cfg, steps=10000):
+    """run `steps` steps of the sine stream with learning on and count, over the last 1000, the steps
+    whose prediction differs from the input that actually came next. A functional known-answer (the hierarchy has learned the
+    wave) on top of the bit-level parity tests."""
+    from ogmaneo2_b200 import streams
+    ins = lambda t: [streams.make(k, t, s) for s, k in zip(cfg["inputSizes"], cfg["streams"])]
+    errs = 0
+    for t in range(steps):
+        h.step(ins(t), True)
+        if t >= steps - 1000:
+            errs += int((h.getPredictionCs(0) != ins(t + 1)[0]).sum())
+    return errs

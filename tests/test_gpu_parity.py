@@ -24,6 +24,18 @@ def test_c1_sine(product, oracle):
     _check(product, oracle, configs.c1_sine(), 400)
 
 
+def test_c1_contract_length_known_answer(product, oracle):
+    """Config 1 at its contract length (10 000 steps, learning on): the number of mispredicted steps among the
+    last 1000 equals the checker's (19 for the reference)."""
+    from common import c1_last1000_errors
+    flat, kind = oracle
+    flat.set_num_threads(1)
+    cfg = configs.c1_sine()
+    want = c1_last1000_errors(maker(flat)(cfg), cfg)
+    got = c1_last1000_errors(maker(product.lib())(cfg), cfg)
+    assert got == want == 19, f"[checker={kind}] product {got}, checker {want}"
+
+
 def test_c2_video_small(product, oracle):
     _check(product, oracle, configs.c2_video(12, 3), 60)
 

@@ -76,6 +76,21 @@ def test_port_vs_reference_side_by_side(name, cfg, steps):
     assert err is None, err
 
 
+def test_c1_learns_the_sine_wave():
+    """Config 1 at its contract length (10 000 steps): the reference mispredicts 19 of the last 1000 steps; the port must
+    give the same count (and the CUDA path too: tests/test_gpu_parity.py::test_c1_contract_length_known_answer)."""
+    from common import c1_last1000_errors
+    cfg = configs.c1_sine()
+    port = loader.port()
+    port.set_num_threads(1)
+    got = c1_last1000_errors(maker(port)(cfg), cfg)
+    ref = loader.ref()
+    if ref is not None:
+        ref.set_num_threads(1)
+        assert got == c1_last1000_errors(maker(ref)(cfg), cfg)
+    assert got == 19
+
+
 def _mask_pad(b: bytes) -> bytes:
     return b  # Int3.pad is zeroed by both writers here (the reference leaves it uninitialised: SURVEY.md D1)
 
